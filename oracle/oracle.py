@@ -207,7 +207,7 @@ def bilateral_params(artifact_smoothing: float) -> Tuple[int, float, float]:
     return d, 30.0, artifact_smoothing * 25               # :410
 
 
-def bilateral(img: np.ndarray, d: int, sigma_color: float, sigma_space: float, use_fma: bool = False) -> np.ndarray:
+def bilateral(img: np.ndarray, d: int, sigma_color: float, sigma_space: float, use_fma: bool = True) -> np.ndarray:
     img = np.ascontiguousarray(img, np.uint8)
     h, w, _ = img.shape
     out = np.empty_like(img)

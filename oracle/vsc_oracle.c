@@ -425,7 +425,9 @@ ORC_API void orc_warp(const float *image, int C, const float *depth, int H, int 
  * cv2.bilateralFilter(src8UC3, d, sigmaColor, sigmaSpace) (stereo_core.py:409-410).
  * OpenCV imgproc/bilateral_filter: radius=max(d/2,1), circular window, L1 colour distance LUT,
  * BORDER_REFLECT_101, float accumulation in tap order, cvRound(sum * (1/wsum)).
- * `use_fma` selects v_muladd-as-FMA accumulation (OpenCV's AVX2/FMA3 dispatch) vs mul+add.
+ * `use_fma` selects v_muladd-as-FMA accumulation (OpenCV's AVX2/FMA3 dispatch, the default here) vs
+ * mul+add.  Pinned against cv2 4.13.0: with IPP disabled the FMA form differs on <= 2e-5 of the
+ * values by 1 LSB (the non-FMA form on ~4e-5); cv2's default IPP build differs from both on ~1.4e-5.
  * ---------------------------------------------------------------------------------------- */
 static inline int reflect101(int i, int n) {
     if (n == 1) return 0;

@@ -1,0 +1,139 @@
+// vsc_common.cuh — shared device helpers for the sm_100a SBS kernels.
+//
+// Float determinism contract: this translation unit is compiled with -fmad=false, so a*b+c is
+// never contracted behind our back; every fused multiply-add below is an explicit fmaf()/fma().
+// The operation order of each float stage is the one the CPU oracle documents, which in turn was
+// identified against torch 2.11 / OpenCV 4.13 (see DESIGN.md "Float order").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsc {
+
+constexpr int kThreads = 256;
+
+struct __align__(16) AxisTap {  // one output coordinate of F.interpolate(bilinear, align_corners=False)
+    int i0, i1;
+    float l0, l1;
+};
+
+struct GaussTaps {  // normalised 1-D Gaussian, k odd, k <= 31 (stereo_core.py:384, :430)
+    int k;
+    float g[31];
+};
+
+struct BilateralTaps {  // cv2.bilateralFilter circular window, radius <= 7 -> <= 149 taps
+    int n;
+    int radius;
+    float w[152];
+    signed char dy[152];
+    signed char dx[152];
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' pad, |pad| < n
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {  // cv2 BORDER_REFLECT_101
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// order-preserving float <-> uint map for atomicMin/atomicMax on floats of either sign
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned u) {
+    unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// ---- CTA-wide byte copies with 128-bit vector accesses where alignment allows -----------------
+// s must satisfy (s & 15) == (g & 15) so that both sides vectorise on the same 16-byte grid.
+__device__ __forceinline__ void cta_copy_g2s(uint8_t* s, const uint8_t* __restrict__ g, int n) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x, nt = blockDim.x * blockDim.y;
+    int head = (int)((16 - ((uintptr_t)g & 15)) & 15);
+    if (head > n) head = n;
+    for (int i = tid; i < head; i += nt) s[i] = g[i];
+    const int nv = (n - head) >> 4;
+    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+    uint4* sv = reinterpret_cast<uint4*>(s + head);
+    for (int i = tid; i < nv; i += nt) sv[i] = __ldg(gv + i);
+    for (int i = head + (nv << 4) + tid; i < n; i += nt) s[i] = g[i];
+}
+__device__ __forceinline__ void cta_copy_s2g(uint8_t* __restrict__ g, const uint8_t* s, int n) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x, nt = blockDim.x * blockDim.y;
+    int head = (int)((16 - ((uintptr_t)g & 15)) & 15);
+    if (head > n) head = n;
+    for (int i = tid; i < head; i += nt) g[i] = s[i];
+    const int nv = (n - head) >> 4;
+    uint4* gv = reinterpret_cast<uint4*>(g + head);
+    const uint4* sv = reinterpret_cast<const uint4*>(s + head);
+    for (int i = tid; i < nv; i += nt) gv[i] = sv[i];
+    for (int i = head + (nv << 4) + tid; i < n; i += nt) g[i] = s[i];
+}
+
+// ---- deterministic pow for apply_depth_gamma (stereo_core.py:107) ------------------------------
+// Same specification as the oracle's orc_powf: only IEEE-754 double +,*,/,fma and exact
+// frexp/ldexp/rint, so CPU and GPU agree bit for bit; the result is the double value rounded to
+// float, i.e. correctly rounded except for ~1e-4 of inputs.
+__device__ __forceinline__ double det_log2(double x) {
+    int e;
+    double m = frexp(x, &e);
+    if (m < 0.70710678118654752440) { m = __dmul_rn(m, 2.0); e -= 1; }
+    const double s = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
+    const double z = __dmul_rn(s, s);
+    double p = 1.0 / 27.0;
+    p = fma(p, z, 1.0 / 25.0);
+    p = fma(p, z, 1.0 / 23.0);
+    p = fma(p, z, 1.0 / 21.0);
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    p = fma(p, z, 1.0);
+    const double ln_m = __dmul_rn(__dmul_rn(2.0, s), p);
+    return fma(ln_m, 1.4426950408889634074, (double)e);
+}
+__device__ __forceinline__ double det_exp2(double t) {
+    const double n = rint(t);
+    const double f = __dmul_rn(__dadd_rn(t, -n), 0.69314718055994530942);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, f, 1.0 / 479001600.0);
+    p = fma(p, f, 1.0 / 39916800.0);
+    p = fma(p, f, 1.0 / 3628800.0);
+    p = fma(p, f, 1.0 / 362880.0);
+    p = fma(p, f, 1.0 / 40320.0);
+    p = fma(p, f, 1.0 / 5040.0);
+    p = fma(p, f, 1.0 / 720.0);
+    p = fma(p, f, 1.0 / 120.0);
+    p = fma(p, f, 1.0 / 24.0);
+    p = fma(p, f, 1.0 / 6.0);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return ldexp(p, (int)n);
+}
+__device__ __forceinline__ float det_powf(float x, float g) {
+    if (g == 2.0f) return __fmul_rn(x, x);
+    if (g == 3.0f) return __fmul_rn(__fmul_rn(x, x), x);
+    if (x == 1.0f) return 1.0f;
+    return (float)det_exp2(__dmul_rn((double)g, det_log2((double)x)));
+}
+
+}  // namespace vsc

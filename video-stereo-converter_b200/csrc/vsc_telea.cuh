@@ -1,0 +1,482 @@
+// vsc_telea.cuh — exact GPU implementation of the reference's hole filling:
+//   cv2.dilate(mask, ones(3,3)) + cv2.inpaint(img, mask, 3, INPAINT_TELEA)
+//   (/root/reference/helper/stereo_core.py:436-457; OpenCV photo/inpaint.cpp).
+//
+// Telea's method is a fast-marching (priority-queue ordered) sweep that re-reads pixels it has just
+// written, so its result depends on the global pop order.  That order only matters between pixels
+// that can see each other (window radius 3 + 1 for gradients, outer distance ring radius 3), so the
+// image is decomposed into independent *clusters* of holes:
+//   1. telea_prepare_kernel   pixel-parallel morphology: M = dilate3x3(hole), band, outer ring,
+//                             initial T, 8x8-tile occupancy and "reaches the kept window" flags
+//   2. tile CCL kernels       union-find connected components over occupied 8x8 tiles; holes in
+//                             different components are >= 15 px apart (> 2*range+2 = 8, the analytic
+//                             independence bound), so components can be marched independently
+//   3. telea_cluster_kernel   one warp per cluster runs the literal sequential algorithm (outer
+//                             ring FMM, then the inpainting FMM); the 28 window taps of a pixel are
+//                             evaluated one per lane and accumulated in the reference's raster order
+// The priority queue (sorted list with FIFO ties in OpenCV) is realised as generations: all queued
+// entries with T in [Tmin, Tmin+0.7) are extracted, sorted by (T, push order) and popped in order;
+// anything pushed meanwhile has T >= popped T + 1/sqrt(2) and therefore belongs to a later
+// generation, so the pop order is identical to the reference's.
+// Clusters with no hole pixel inside the kept (convergence-cropped) column window are skipped:
+// their pixels are never read by the back end.
+#pragma once
+#include "vsc_kernels.cuh"
+
+namespace vsc {
+
+// state byte per pixel: bits 0-1 f (Telea flags), bits 2-3 o (outer-ring flags), bit 4 initial band
+enum : unsigned char { F_KNOWN = 0, F_BAND = 1, F_INSIDE = 2, F_MASK = 3, O_BAND = 1 << 2, O_INSIDE = 2 << 2,
+                       O_CHANGE = 3 << 2, O_MASK = 3 << 2, ST_BAND0 = 1 << 4 };
+
+constexpr int TG = 8;   // tile edge for clustering
+
+struct TeleaView {
+    uchar4* img;            // [Hs][Ws] in/out (alpha = validity from the warp)
+    const uint8_t* valid;   // [Hs][Ws] 1 = valid (compact copy of alpha)
+    uint8_t* st;            // [Hs][Ws]
+    float* tt;              // [Hs][Ws]
+    // tile grid
+    unsigned char* tile_cnt;   // [th*tw] number of M|band|ring pixels (<= 64)
+    unsigned char* tile_need;  // [th*tw] tile has an M pixel inside the kept window
+    int* lab;                  // [th*tw] union-find parent, -1 = empty tile
+    int* csize;                // [th*tw] per-root pixel count
+    int* ctiles;               // [th*tw] per-root tile count
+    int* cneed;                // [th*tw] per-root needed flag
+    int* cslot;                // [th*tw] per-root cluster slot
+    // clusters
+    int* cl_qoff;  int* cl_toff;  int* cl_ntiles;  int* cl_size;  int* cl_fill;
+    int* tile_list;            // [ntiles_active]
+    unsigned long long* qkey[2];   // pool / current generation keys
+    unsigned* qidx[2];
+    int qcap;
+};
+
+struct TeleaArgs {
+    TeleaView v[2];
+    FrameScalars* fs;
+    int Hs, Ws, tw, th;
+    int keep_x0[2], keep_x1[2];
+    int nviews;
+};
+
+// ---- 1. morphology ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_constant__ TeleaArgs a) {
+    __shared__ unsigned char h0[42][44];   // hole0 (apron 5)
+    __shared__ unsigned char M[40][44];    // dilated mask (apron 4)
+    __shared__ int cnt[16], need[16];
+    const int v = blockIdx.z;
+    const TeleaView& V = a.v[v];
+    const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 16) { cnt[tid] = 0; need[tid] = 0; }
+    for (int i = tid; i < 42 * 42; i += kThreads) {
+        const int iy = i / 42, ix = i - iy * 42;
+        const int y = Y0 - 5 + iy, x = X0 - 5 + ix;
+        unsigned char h = 0;
+        if (y >= 0 && y < a.Hs && x >= 0 && x < a.Ws) h = V.valid[(size_t)y * a.Ws + x] ? 0 : 1;
+        h0[iy][ix] = h;
+    }
+    __syncthreads();
+    for (int i = tid; i < 40 * 40; i += kThreads) {
+        const int iy = i / 40, ix = i - iy * 40;   // M coords: image (Y0-4+iy, X0-4+ix) = h0 (iy+1, ix+1)
+        const int y = Y0 - 4 + iy, x = X0 - 4 + ix;
+        unsigned char m = 0;
+        if (y >= 0 && y < a.Hs && x >= 0 && x < a.Ws) {
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) m |= h0[iy + dy][ix + dx];
+        }
+        M[iy][ix] = m;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int ly = threadIdx.y + 8 * j, lx = threadIdx.x;
+        const int y = Y0 + ly, x = X0 + lx;
+        if (y >= a.Hs || x >= a.Ws) continue;
+        const int my = ly + 4, mx = lx + 4;
+        const unsigned char m = M[my][mx];
+        const unsigned char band = !m && (M[my - 1][mx] | M[my + 1][mx] | M[my][mx - 1] | M[my][mx + 1]);
+        unsigned char near3 = 0, near4 = 0;
+        for (int dy = -4; dy <= 4; dy++)
+            for (int dx = -4; dx <= 4; dx++) {
+                const unsigned char q = M[my + dy][mx + dx];
+                near4 |= q;
+                if (dy >= -3 && dy <= 3 && dx >= -3 && dx <= 3) near3 |= q;
+            }
+        const unsigned char ring = !m && !band && near3;
+        const size_t p = (size_t)y * a.Ws + x;
+        V.st[p] = (m ? F_INSIDE : 0) | (ring ? O_INSIDE : 0) | (band ? ST_BAND0 : 0);
+        if (near4) V.tt[p] = band ? 0.f : 1.0e6f;
+        if (m | band | ring) {
+            const int t = (ly >> 3) * 4 + (lx >> 3);
+            atomicAdd(&cnt[t], 1);
+            if (m && x >= a.keep_x0[v] && x < a.keep_x1[v]) need[t] = 1;
+        }
+    }
+    __syncthreads();
+    if (tid < 16) {
+        const int ty = blockIdx.y * 4 + (tid >> 2), tx = blockIdx.x * 4 + (tid & 3);
+        if (ty < a.th && tx < a.tw) {
+            V.tile_cnt[ty * a.tw + tx] = (unsigned char)cnt[tid];
+            V.tile_need[ty * a.tw + tx] = (unsigned char)need[tid];
+        }
+    }
+}
+
+// ---- 2. connected components over occupied tiles (8-connectivity, union-find) -------------------
+__device__ __forceinline__ int uf_find(int* lab, int x) {
+    int p = lab[x];
+    while (p != x) { x = p; p = lab[x]; }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* lab, int a, int b) {
+    while (true) {
+        a = uf_find(lab, a);
+        b = uf_find(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void telea_ccl_init_kernel(const __grid_constant__ TeleaArgs a) {
+    const int n = a.tw * a.th;
+    for (int v = 0; v < a.nviews; v++) {
+        const TeleaView& V = a.v[v];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            V.lab[t] = V.tile_cnt[t] ? t : -1;
+            V.csize[t] = 0; V.ctiles[t] = 0; V.cneed[t] = 0; V.cslot[t] = -1;
+        }
+    }
+}
+__global__ void telea_ccl_merge_kernel(const __grid_constant__ TeleaArgs a) {
+    const int n = a.tw * a.th;
+    for (int v = 0; v < a.nviews; v++) {
+        const TeleaView& V = a.v[v];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            if (V.lab[t] < 0) continue;
+            const int ty = t / a.tw, tx = t - ty * a.tw;
+            if (tx > 0 && V.tile_cnt[t - 1]) uf_union(V.lab, t, t - 1);
+            if (ty > 0) {
+                if (V.tile_cnt[t - a.tw]) uf_union(V.lab, t, t - a.tw);
+                if (tx > 0 && V.tile_cnt[t - a.tw - 1]) uf_union(V.lab, t, t - a.tw - 1);
+                if (tx + 1 < a.tw && V.tile_cnt[t - a.tw + 1]) uf_union(V.lab, t, t - a.tw + 1);
+            }
+        }
+    }
+}
+__global__ void telea_ccl_flatten_kernel(const __grid_constant__ TeleaArgs a) {
+    const int n = a.tw * a.th;
+    for (int v = 0; v < a.nviews; v++) {
+        const TeleaView& V = a.v[v];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            if (V.lab[t] < 0) continue;
+            const int root = uf_find(V.lab, t);
+            atomicAdd(&V.csize[root], (int)V.tile_cnt[t]);
+            atomicAdd(&V.ctiles[root], 1);
+            if (V.tile_need[t]) atomicOr(&V.cneed[root], 1);
+        }
+    }
+}
+__global__ void telea_cluster_alloc_kernel(const __grid_constant__ TeleaArgs a) {
+    const int n = a.tw * a.th;
+    for (int v = 0; v < a.nviews; v++) {
+        const TeleaView& V = a.v[v];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            if (V.lab[t] != t || !V.cneed[t]) continue;
+            const int ci = atomicAdd(&a.fs->ncl[v], 1);
+            V.cl_qoff[ci] = atomicAdd(&a.fs->qbump[v], V.csize[t]);
+            V.cl_toff[ci] = atomicAdd(&a.fs->tbump[v], V.ctiles[t]);
+            V.cl_ntiles[ci] = V.ctiles[t];
+            V.cl_size[ci] = V.csize[t];
+            V.cl_fill[ci] = 0;
+            V.cslot[t] = ci;
+        }
+    }
+}
+__global__ void telea_cluster_fill_kernel(const __grid_constant__ TeleaArgs a) {
+    const int n = a.tw * a.th;
+    for (int v = 0; v < a.nviews; v++) {
+        const TeleaView& V = a.v[v];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            if (V.lab[t] < 0) continue;
+            const int root = uf_find(V.lab, t);
+            const int ci = V.cslot[root];
+            if (ci < 0) continue;
+            const int pos = atomicAdd(&V.cl_fill[ci], 1);
+            V.tile_list[V.cl_toff[ci] + pos] = t;
+        }
+    }
+}
+
+// ---- 3. per-cluster sequential march, one warp per cluster ---------------------------------------
+struct TapConst { signed char dk[32]; signed char dl[32]; float dst[32]; };
+__constant__ TapConst c_taps;   // 28 taps of the radius-3 disc in k-major raster order (centre excluded)
+
+struct Marcher {
+    const TeleaView& V;
+    int Hs, Ws;
+    int lane;
+    __device__ __forceinline__ bool inb(int y, int x) const { return y >= 0 && y < Hs && x >= 0 && x < Ws; }
+    // flags / T with the 1-pixel KNOWN frame (t = 1e6) that cv2.inpaint adds around the image
+    template <bool OUTER> __device__ __forceinline__ bool inside(int y, int x) const {
+        if (!inb(y, x)) return false;
+        const unsigned char s = V.st[(size_t)y * Ws + x];
+        return OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE);
+    }
+    __device__ __forceinline__ float T_raw(int y, int x) const { return inb(y, x) ? V.tt[(size_t)y * Ws + x] : 1.0e6f; }
+    // T as the inpainting pass sees it: the outer pass' distances are negated (icvCalcFMM negate=true)
+    __device__ __forceinline__ float T_main(int y, int x) const {
+        if (!inb(y, x)) return 1.0e6f;
+        const size_t p = (size_t)y * Ws + x;
+        const float t = V.tt[p];
+        return ((V.st[p] & O_MASK) == O_CHANGE) ? -t : t;
+    }
+    template <bool OUTER> __device__ __forceinline__ float solve(int y1, int x1, int y2, int x2) const {
+        const double a11 = OUTER ? T_raw(y1, x1) : T_main(y1, x1), a22 = OUTER ? T_raw(y2, x2) : T_main(y2, x2);
+        const double m12 = a11 < a22 ? a11 : a22;
+        double sol;
+        if (!inside<OUTER>(y1, x1)) {
+            if (!inside<OUTER>(y2, x2)) {
+                const double d = __dadd_rn(a11, -a22);
+                if (fabs(d) >= 1.0) sol = __dadd_rn(1.0, m12);
+                else sol = __dmul_rn(__dadd_rn(__dadd_rn(a11, a22), sqrt(__dadd_rn(2.0, -__dmul_rn(d, d)))), 0.5);
+            } else sol = __dadd_rn(1.0, a11);
+        } else if (!inside<OUTER>(y2, x2)) sol = __dadd_rn(1.0, a22);
+        else sol = __dadd_rn(1.0, m12);
+        return (float)sol;
+    }
+    template <bool OUTER> __device__ __forceinline__ float min4(int y, int x) const {
+        const float s0 = solve<OUTER>(y - 1, x, y, x - 1), s1 = solve<OUTER>(y + 1, x, y, x - 1);
+        const float s2 = solve<OUTER>(y - 1, x, y, x + 1), s3 = solve<OUTER>(y + 1, x, y, x + 1);
+        return fminf(fminf(s0, s1), fminf(s2, s3));
+    }
+    __device__ __forceinline__ int pix(int y, int x, int c) const {
+        const uchar4 p = V.img[(size_t)y * Ws + x];
+        return c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    }
+    // icvTeleaInpaintFMM body for one pixel (y,x) whose T was just set to `dist`; warp-cooperative
+    __device__ void inpaint(int y, int x, float dist, float* sm /* [28][10] */) const {
+        // gradT (warp-uniform)
+        float gtx, gty;
+        {
+            const bool r = !inside<false>(y, x + 1), l = !inside<false>(y, x - 1);
+            const bool d = !inside<false>(y + 1, x), u = !inside<false>(y - 1, x);
+            if (r) gtx = l ? __fmul_rn(__fsub_rn(T_main(y, x + 1), T_main(y, x - 1)), 0.5f) : __fsub_rn(T_main(y, x + 1), dist);
+            else gtx = l ? __fsub_rn(dist, T_main(y, x - 1)) : 0.f;
+            if (d) gty = u ? __fmul_rn(__fsub_rn(T_main(y + 1, x), T_main(y - 1, x)), 0.5f) : __fsub_rn(T_main(y + 1, x), dist);
+            else gty = u ? __fsub_rn(dist, T_main(y - 1, x)) : 0.f;
+        }
+        bool valid = false;
+        float term[10];
+        if (lane < 28) {
+            const int dk = c_taps.dk[lane], dl = c_taps.dl[lane];
+            const int ky = y + dk, kx = x + dl;
+            if (inb(ky, kx) && !inside<false>(ky, kx)) {
+                valid = true;
+                const float ry = (float)(-dk), rx = (float)(-dl);
+                const float dst = c_taps.dst[lane];
+                const float lev = (float)__ddiv_rn(1.0, __dadd_rn(1.0, fabs((double)__fsub_rn(T_main(ky, kx), dist))));
+                float dir = __fadd_rn(__fmul_rn(rx, gtx), __fmul_rn(ry, gty));
+                if (fabs((double)dir) <= 0.01) dir = 0.000001f;
+                const float w = fabsf(__fmul_rn(__fmul_rn(dst, lev), dir));
+                const bool fr = !inside<false>(ky, kx + 1), fl = !inside<false>(ky, kx - 1);
+                const bool fd = !inside<false>(ky + 1, kx), fu = !inside<false>(ky - 1, kx);
+                const int km = ky + (ky == 0), kp = ky - (ky == Hs - 1);
+                const int lm = kx + (kx == 0), lp = kx - (kx == Ws - 1);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float gix, giy;
+                    if (fr) gix = fl ? __fmul_rn((float)(pix(km, lp + 1, c) - pix(km, lm - 1, c)), 2.0f)
+                                     : (float)(pix(km, lp + 1, c) - pix(km, lm, c));
+                    else gix = fl ? (float)(pix(km, lp, c) - pix(km, lm - 1, c)) : 0.f;
+                    if (fd) giy = fu ? __fmul_rn((float)(pix(kp + 1, lm, c) - pix(km - 1, lm, c)), 2.0f)
+                                     : (float)(pix(kp + 1, lm, c) - pix(km, lm, c));
+                    else giy = fu ? (float)(pix(kp, lm, c) - pix(km - 1, lm, c)) : 0.f;
+                    term[c] = __fmul_rn(w, (float)pix(ky, kx, c));
+                    term[3 + c] = __fmul_rn(w, __fmul_rn(gix, rx));
+                    term[6 + c] = __fmul_rn(w, __fmul_rn(giy, ry));
+                }
+                term[9] = w;
+            }
+        }
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 10; q++) sm[lane * 10 + q] = term[q];
+        }
+        __syncwarp();
+        // lanes 0..9 each accumulate one quantity in tap (raster) order: Ia[3], Jx[3], Jy[3], s
+        float acc = lane == 9 ? 1.0e-20f : 0.f;
+        if (lane < 10) {
+            const bool sub = lane >= 3 && lane < 9;
+            for (unsigned m = vm; m; m &= m - 1) {
+                const int L = __ffs(m) - 1;
+                const float t = sm[L * 10 + lane];
+                acc = sub ? __fsub_rn(acc, t) : __fadd_rn(acc, t);
+            }
+        }
+        const float s = __shfl_sync(0xffffffffu, acc, 9);
+        const float jx = __shfl_sync(0xffffffffu, acc, min(lane + 3, 31));
+        const float jy = __shfl_sync(0xffffffffu, acc, min(lane + 6, 31));
+        int outc = 0;
+        if (lane < 3) {
+            const float ia_s = __fdiv_rn(acc, s);
+            const float jsum = __fadd_rn(jx, jy);
+            const float jn = __fadd_rn(__fmul_rn(jx, jx), __fmul_rn(jy, jy));
+            const double den = __dadd_rn(sqrt((double)jn), (double)1.0e-20f);
+            const double val = __dadd_rn(__dadd_rn((double)ia_s, __ddiv_rn((double)jsum, den)), (double)0.5f);
+            const float sat = (float)val;
+            outc = min(max(__float2int_rn(sat), 0), 255);
+        }
+        const int c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
+                  c2 = __shfl_sync(0xffffffffu, outc, 2);
+        __syncwarp();
+        if (lane == 0) {
+            uchar4 p = V.img[(size_t)y * Ws + x];
+            p.x = (unsigned char)c0; p.y = (unsigned char)c1; p.z = (unsigned char)c2;
+            V.img[(size_t)y * Ws + x] = p;
+        }
+    }
+};
+
+// warp-wide bitonic sort of n (key,idx) pairs in global memory, ascending by key.  All compare-exchanges are
+// ascending (the "flip" formulation), so the virtual +inf padding above n never has to move and pairs whose
+// partner is >= n can simply be skipped.
+__device__ __forceinline__ void cmpswap(unsigned long long* key, unsigned* idx, int i, int p) {
+    const unsigned long long a = key[i], b = key[p];
+    if (a > b) {
+        key[i] = b; key[p] = a;
+        const unsigned t = idx[i]; idx[i] = idx[p]; idx[p] = t;
+    }
+}
+__device__ void warp_sort(unsigned long long* key, unsigned* idx, int n, int lane) {
+    if (n <= 1) return;
+    int N = 1;
+    while (N < n) N <<= 1;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int i = lane; i < n; i += 32) {
+            const int p = i ^ (k - 1);
+            if (p > i && p < n) cmpswap(key, idx, i, p);
+        }
+        __syncwarp();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                const int p = i ^ j;
+                if (p > i && p < n) cmpswap(key, idx, i, p);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <bool OUTER>
+__device__ void march(const Marcher& mc, const TeleaView& V, int qoff, int ntiles, const int* tiles, int tw,
+                      float* sm, int lane) {
+    unsigned long long* pool_k = V.qkey[0] + qoff;  unsigned* pool_i = V.qidx[0] + qoff;
+    unsigned long long* cur_k = V.qkey[1] + qoff;   unsigned* cur_i = V.qidx[1] + qoff;
+    const int Ws = mc.Ws, Hs = mc.Hs;
+    int npool = 0;
+    // initial queue: the band pixels (T = 0) in raster order == ascending linear index
+    for (int ti = 0; ti < ntiles; ti++) {
+        const int t = tiles[ti];
+        const int ty = t / tw, tx = t - ty * tw;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int y = ty * TG + (lane >> 3) + 4 * h, x = tx * TG + (lane & 7);
+            bool isb = false;
+            unsigned p = 0;
+            if (y < Hs && x < Ws) { p = (unsigned)y * (unsigned)Ws + (unsigned)x; isb = (V.st[p] & ST_BAND0) != 0; }
+            const unsigned bm = __ballot_sync(0xffffffffu, isb);
+            if (isb) {
+                const int pos = npool + __popc(bm & ((1u << lane) - 1));
+                pool_k[pos] = (unsigned long long)p;   // T bits = 0
+                pool_i[pos] = p;
+            }
+            npool += __popc(bm);
+        }
+    }
+    __syncwarp();
+    unsigned seq = 0;
+    while (npool > 0) {
+        // generation = entries with T < Tmin + 0.7
+        unsigned tmin = 0xffffffffu;
+        for (int i = lane; i < npool; i += 32) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
+        tmin = __reduce_min_sync(0xffffffffu, tmin);
+        const float thr = __uint_as_float(tmin) + 0.7f;
+        int ncur = 0, nkeep = 0;
+        for (int base = 0; base < npool; base += 32) {
+            const int i = base + lane;
+            unsigned long long k = 0; unsigned p = 0;
+            bool have = i < npool, sel = false;
+            if (have) { k = pool_k[i]; p = pool_i[i]; sel = __uint_as_float((unsigned)(k >> 32)) < thr; }
+            const unsigned ms = __ballot_sync(0xffffffffu, have && sel), mk = __ballot_sync(0xffffffffu, have && !sel);
+            __syncwarp();
+            if (have && sel) { const int pos = ncur + __popc(ms & ((1u << lane) - 1)); cur_k[pos] = k; cur_i[pos] = p; }
+            if (have && !sel) { const int pos = nkeep + __popc(mk & ((1u << lane) - 1)); pool_k[pos] = k; pool_i[pos] = p; }
+            ncur += __popc(ms); nkeep += __popc(mk);
+            __syncwarp();
+        }
+        npool = nkeep;
+        warp_sort(cur_k, cur_i, ncur, lane);
+        __syncwarp();
+        for (int e = 0; e < ncur; e++) {
+            const unsigned p = cur_i[e];
+            const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
+            if (OUTER && lane == 0) V.st[p] = (V.st[p] & ~O_MASK) | O_CHANGE;
+            __syncwarp();
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
+                if (!mc.inb(y, x)) continue;
+                if (!mc.inside<OUTER>(y, x)) continue;
+                const size_t pn = (size_t)y * Ws + x;
+                const float dist = mc.min4<OUTER>(y, x);
+                if (lane == 0) V.tt[pn] = dist;
+                __syncwarp();
+                if (!OUTER) mc.inpaint(y, x, dist, sm);
+                if (lane == 0) {
+                    const unsigned char s = V.st[pn];
+                    V.st[pn] = OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND);
+                    pool_k[npool] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)seq;
+                    pool_i[npool] = (unsigned)pn;
+                }
+                npool++; seq++;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+constexpr int TELEA_WARPS = 4;
+__global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
+    __shared__ float sm_all[TELEA_WARPS][28 * 10];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int v = blockIdx.y;
+    const TeleaView& V = a.v[v];
+    const int ncl = a.fs->ncl[v];
+    if (a.fs->qbump[v] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&a.fs->overflow, a.fs->qbump[v]);
+        return;
+    }
+    Marcher mc{V, a.Hs, a.Ws, lane};
+    while (true) {
+        int ci = 0;
+        if (lane == 0) ci = atomicAdd(&a.fs->next[v], 1);
+        ci = __shfl_sync(0xffffffffu, ci, 0);
+        if (ci >= ncl) break;
+        const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
+        const int* tiles = V.tile_list + V.cl_toff[ci];
+        march<true>(mc, V, qoff, ntiles, tiles, a.tw, sm_all[wid], lane);
+        __syncwarp();
+        march<false>(mc, V, qoff, ntiles, tiles, a.tw, sm_all[wid], lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace vsc

@@ -1,0 +1,263 @@
+"""Drop-in for the reference's `helper/stereo_core.py` on top of libvsc_b200.so.
+
+Same `__all__`, same signatures, same defaults and the same error behaviour for the hot call as
+/root/reference/helper/stereo_core.py:22-29, :193-311 — the arithmetic runs in hand-written
+sm_100a CUDA kernels behind the C ABI of include/vsc_b200.h.  There is no CPU path:
+`StereoGenerator('cpu')` raises, and a missing CUDA library raises on import of `_lib`.
+
+Additions that the reference does not have (used by the frame loop in sbs_generator.py):
+`StereoGenerator.submit/collect` (asynchronous, pinned, multi-slot) and `process_batch`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    'load_image_pair',
+    'normalize_depth',
+    'apply_depth_gamma',
+    'forward_warp_stereo',
+    'StereoParams',
+    'StereoGenerator',
+]
+
+
+@dataclass
+class StereoParams:
+    """Parameters for stereo image generation (reference: stereo_core.py:193-202; config.json
+    `stereo` block, helper/config_manager.py:43-54)."""
+    max_disparity: float = 50.0
+    convergence: float = -10.0
+    super_sampling: float = 3.0
+    edge_softness: float = 20.0
+    artifact_smoothing: float = 1.0
+    depth_gamma: float = 0.2
+    sharpen: float = 14.0
+
+
+# ------------------------------------------------------------------------------------------------
+# file loading (reference: stereo_core.py:32-68) — plain OpenCV I/O, not part of the GPU path
+# ------------------------------------------------------------------------------------------------
+def load_image_pair(rgb_path: Path, depth_path: Path) -> Tuple[np.ndarray, np.ndarray]:
+    """Load an RGB frame and its depth map; raises ValueError when a file cannot be read."""
+    import cv2
+    rgb = cv2.imread(str(rgb_path), cv2.IMREAD_COLOR)
+    depth = cv2.imread(str(depth_path), cv2.IMREAD_UNCHANGED)
+    if rgb is None:
+        raise ValueError(f'Could not load RGB: {rgb_path}')
+    if depth is None:
+        raise ValueError(f'Could not load depth: {depth_path}')
+    if depth.ndim == 3:
+        depth = cv2.cvtColor(depth, cv2.COLOR_BGR2GRAY)
+    if rgb.shape[:2] != depth.shape[:2]:
+        depth = _resize_depth_to(depth, rgb.shape[1], rgb.shape[0])
+    return cv2.cvtColor(rgb, cv2.COLOR_BGR2RGB), depth
+
+
+def _resize_depth_to(depth: np.ndarray, w: int, h: int) -> np.ndarray:
+    """Size-mismatch branch of load_image_pair (stereo_core.py:64-65): LANCZOS4 to the frame size."""
+    import cv2
+    return cv2.resize(depth, (w, h), interpolation=cv2.INTER_LANCZOS4)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared default context for the module-level helpers
+# ------------------------------------------------------------------------------------------------
+_default_ctx: Optional[_lib.Context] = None
+
+
+def _ctx() -> _lib.Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = _lib.Context(_current_device(), 1)
+    return _default_ctx
+
+
+def _current_device() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return 0
+
+
+def _as_f32(t):
+    """torch tensor -> contiguous float32 numpy on host (+ a function to map results back)."""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('expected a torch.Tensor')
+    dev, dt = t.device, t.dtype
+    a = np.ascontiguousarray(t.detach().to('cpu', torch.float32).numpy())
+
+    def back(x: np.ndarray):
+        return torch.from_numpy(x).to(device=dev, dtype=dt)
+    return a, back
+
+
+def normalize_depth(depth):
+    """Normalize depth to [0, 1] (reference: stereo_core.py:71-88); zeros if the range is < 1e-6."""
+    a, back = _as_f32(depth)
+    out = np.empty_like(a)
+    _lib.check(_lib.load().vsc_stage_normalize_f32(_ctx().handle, _lib.ptr(a), a.size, _lib.ptr(out)))
+    return back(out)
+
+
+def apply_depth_gamma(depth, gamma: float):
+    """pow(clamp(depth, 0.001, 1), gamma) (reference: stereo_core.py:91-107)."""
+    a, back = _as_f32(depth)
+    out = np.empty_like(a)
+    _lib.check(_lib.load().vsc_stage_gamma_f32(_ctx().handle, _lib.ptr(a), a.size, float(gamma), _lib.ptr(out)))
+    return back(out)
+
+
+def forward_warp_stereo(image, depth, max_disparity: float):
+    """Left/right forward warp with occlusion ordering (reference: stereo_core.py:110-190).
+
+    image [1, C, H, W], depth [1, 1, H, W] -> (left, left_mask, right, right_mask) with the
+    reference's shapes [1, C, H, W] / [1, 1, H, W].  B must be 1, as in the reference (:146).
+    """
+    if image.dim() != 4 or image.shape[0] != 1:
+        raise RuntimeError('forward_warp_stereo requires a [1, C, H, W] image (the reference views it as [C, -1])')
+    img, back = _as_f32(image)
+    dep, _ = _as_f32(depth)
+    _, c, h, w = img.shape
+    if dep.size != h * w:
+        raise RuntimeError('depth must have H*W elements')
+    left, right = np.empty((1, c, h, w), np.float32), np.empty((1, c, h, w), np.float32)
+    lm, rm = np.empty((1, 1, h, w), np.float32), np.empty((1, 1, h, w), np.float32)
+    _lib.check(_lib.load().vsc_stage_warp_f32(_ctx().handle, _lib.ptr(img), _lib.ptr(dep), c, h, w, float(max_disparity),
+                                              _lib.ptr(left), _lib.ptr(lm), _lib.ptr(right), _lib.ptr(rm)))
+    return back(left), back(lm), back(right), back(rm)
+
+
+# ------------------------------------------------------------------------------------------------
+# the generator
+# ------------------------------------------------------------------------------------------------
+def _parse_device(device: str) -> int:
+    dev = str(device)
+    if dev == 'cuda':
+        return _current_device()
+    if dev.startswith('cuda:'):
+        return int(dev.split(':', 1)[1])
+    raise RuntimeError(
+        f"StereoGenerator(device={device!r}): the B200 SBS path runs on CUDA only and has no CPU fallback; "
+        "use the reference implementation for CPU processing")
+
+
+class StereoGenerator:
+    """Batch processor for stereo SBS image generation (reference: stereo_core.py:205-311).
+
+    `process_frame(rgb, depth, params)` keeps the reference's numpy-in / numpy-out contract.
+    `n_slots` frames can be in flight through `submit` / `collect` for the driver loop.
+    """
+    _DEFAULT_PARAMS = StereoParams()
+
+    def __init__(self, device: str, n_slots: int = 1) -> None:
+        self.device = device
+        self._ctx = _lib.Context(_parse_device(device), n_slots)
+        self._lib = _lib.load()
+        self.n_slots = n_slots
+        self._pending = [None] * n_slots        # per slot: (out array, owner tuple keeping inputs alive)
+        self._pinned = [None] * n_slots         # per slot: (key, rgb PinnedBuffer, depth PinnedBuffer, out PinnedBuffer)
+
+    # -- reference API ---------------------------------------------------------------------------
+    def process_frame(self, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> np.ndarray:
+        """Process a single frame to a side-by-side stereo image (left | right), uint8 [H, 2W, 3]."""
+        p = params or self._DEFAULT_PARAMS
+        rgb_c, depth_c, code = self._check_inputs(rgb, depth)
+        h, w = rgb_c.shape[:2]
+        out = np.empty((h, 2 * w, 3), np.uint8)
+        _lib.check(self._lib.vsc_process_frame(self._ctx.handle, _lib.ptr(rgb_c), _lib.ptr(depth_c), code, h, w,
+                                               C.byref(_lib.make_params(p)), _lib.ptr(out)))
+        return out
+
+    # -- asynchronous pipeline ---------------------------------------------------------------------
+    def submit(self, slot: int, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> None:
+        """Copy the frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
+        p = params or self._DEFAULT_PARAMS
+        if self._pending[slot] is not None:
+            raise RuntimeError(f'slot {slot} has an uncollected frame')
+        rgb_c, depth_c, code = self._check_inputs(rgb, depth)
+        h, w = rgb_c.shape[:2]
+        key = (h, w, depth_c.dtype.str)
+        pin = self._pinned[slot]
+        if pin is None or pin[0] != key:
+            if pin is not None:
+                for b in pin[1:]:
+                    b.free()
+            pin = (key, _lib.PinnedBuffer((h, w, 3), np.uint8), _lib.PinnedBuffer((h, w), depth_c.dtype),
+                   _lib.PinnedBuffer((h, 2 * w, 3), np.uint8))
+            self._pinned[slot] = pin
+        np.copyto(pin[1].array, rgb_c)
+        np.copyto(pin[2].array, depth_c)
+        _lib.check(self._lib.vsc_submit(self._ctx.handle, slot, _lib.ptr(pin[1].array), _lib.ptr(pin[2].array), code, h, w,
+                                        C.byref(_lib.make_params(p)), _lib.ptr(pin[3].array)))
+        self._pending[slot] = (h, w)
+
+    def collect(self, slot: int) -> np.ndarray:
+        """Wait for the slot's frame and return a fresh array the caller owns (the reference hands
+        its result to another thread, sbs_generator.py:325, so it must not alias a reused buffer)."""
+        if self._pending[slot] is None:
+            raise RuntimeError(f'slot {slot} has no frame in flight')
+        try:
+            _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
+        finally:
+            self._pending[slot] = None
+        return self._pinned[slot][3].array.copy()
+
+    def process_batch(self, frames: Iterable[Tuple[np.ndarray, np.ndarray]],
+                      params: StereoParams | None = None) -> List[np.ndarray]:
+        """Run an iterable of (rgb, depth) through all slots, keeping `n_slots` frames in flight."""
+        out: List[np.ndarray] = []
+        inflight: List[int] = []
+        nxt = 0
+        for rgb, depth in frames:
+            if len(inflight) == self.n_slots:
+                out.append(self.collect(inflight.pop(0)))
+            self.submit(nxt, rgb, depth, params)
+            inflight.append(nxt)
+            nxt = (nxt + 1) % self.n_slots
+        while inflight:
+            out.append(self.collect(inflight.pop(0)))
+        return out
+
+    def last_frame_ms(self, slot: int = 0) -> float:
+        ms = C.c_float()
+        _lib.check(self._lib.vsc_slot_elapsed_ms(self._ctx.handle, slot, C.byref(ms)))
+        return float(ms.value)
+
+    def last_frame_launches(self, slot: int = 0) -> int:
+        return int(self._lib.vsc_slot_launches(self._ctx.handle, slot))
+
+    def close(self) -> None:
+        for pin in self._pinned:
+            if pin is not None:
+                for b in pin[1:]:
+                    b.free()
+        self._pinned = [None] * self.n_slots
+        self._ctx.close()
+
+    # -- helpers -----------------------------------------------------------------------------------
+    @staticmethod
+    def _check_inputs(rgb: np.ndarray, depth: np.ndarray):
+        if rgb.ndim != 3 or rgb.shape[2] != 3:
+            raise ValueError(f'rgb must be [H, W, 3], got {rgb.shape}')
+        if rgb.dtype != np.uint8:
+            rgb = rgb.astype(np.uint8)
+        if depth.ndim != 2:
+            raise ValueError(f'depth must be [H, W], got {depth.shape}')
+        if depth.shape != rgb.shape[:2]:
+            raise ValueError(f'depth {depth.shape} does not match frame {rgb.shape[:2]}')
+        if depth.dtype not in (np.uint8, np.uint16, np.float32):
+            # the reference casts any numeric dtype to float32 after cv2.resize (stereo_core.py:328)
+            depth = depth.astype(np.float32)
+        return np.ascontiguousarray(rgb), np.ascontiguousarray(depth), _lib.depth_code(depth.dtype)
