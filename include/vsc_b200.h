@@ -146,6 +146,19 @@ int vsc_stage_gamma_f32(vsc_ctx *ctx, const float *in, size_t n, double gamma, f
 int vsc_stage_warp_f32(vsc_ctx *ctx, const float *image, const float *depth, int channels, int height, int width,
                        double max_disparity, float *left, float *left_mask, float *right, float *right_mask);
 
+/* -------- measurement / debugging helpers (no reference counterpart) -------------------------- */
+/* record an event pair around every kernel launch of subsequently submitted frames */
+int vsc_set_profiling(vsc_ctx *ctx, int on);
+/* names and device milliseconds of the kernels of the last completed frame on `slot`; returns count */
+int vsc_slot_kernel_times(vsc_ctx *ctx, int slot, int max_n, const char **names, float *ms);
+/* device timer across all slot streams (CUDA events): begin gates every slot stream on a start
+ * event, end records once every slot stream has drained and returns the elapsed milliseconds */
+int vsc_timer_begin(vsc_ctx *ctx);
+int vsc_timer_end(vsc_ctx *ctx, float *ms);
+/* copies of slot 0's intermediates / Telea state after a completed call, for stage bisection in tests */
+int vsc_debug_fetch(vsc_ctx *ctx, int which, void *dst, size_t bytes);
+int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,7 @@ def test_near_black_quirk(gen):
     _, depth = make_pair(64, 96, seed=3)
     out = gen.process_frame(rgb, depth)
     assert np.array_equal(out, O.process_frame(rgb, depth))
-    assert (out == 255).all()
+    assert (out >= 254).all()      # the x255 branch was taken (torch 2.11 gives 254 after the unsharp round trip)
     out0 = gen.process_frame(rgb, depth, StereoParams(artifact_smoothing=0.0))
     assert np.array_equal(out0, O.process_frame(rgb, depth, O.Params(artifact_smoothing=0.0)))
 
@@ -118,33 +118,32 @@ def test_module_level_helpers():
     assert np.array_equal(lm[0, 0].numpy().astype(np.uint8), olm) and np.array_equal(rm[0, 0].numpy().astype(np.uint8), orm)
 
 
-# ---- benchmark sizes: properties that do not need the (slow) oracle --------------------------------
-@pytest.mark.parametrize('h,w,dt', [(1080, 1920, np.uint8), (2160, 3840, np.uint16)])
-def test_full_size_properties(gen, h, w, dt):
+# ---- benchmark sizes ---------------------------------------------------------------------------
+def _compare_full(gen, h, w, dt, kw):
     rgb, depth = make_pair(h, w, seed=0, depth_dtype=dt)
-    a = gen.process_frame(rgb, depth)
-    assert a.shape == (h, 2 * w, 3)
-    assert np.array_equal(a, gen.process_frame(rgb, depth)), 'not deterministic'
-    # horizontal mirror symmetry of the algorithm: mirroring the inputs swaps and mirrors the eyes,
-    # up to the asymmetry of the crop geometry; with convergence 0 and an even buffer the swap is exact
-    p = StereoParams(convergence=0.0)
-    o1 = gen.process_frame(rgb, depth, p)
-    # flat depth => both eyes are the same shifted copy => left half == right half shifted by geometry;
-    # check instead that a flat-depth frame has no holes left (no zero runs) and is bit-stable
-    flat = np.full((h, w), 5, dt)
-    o2 = gen.process_frame(rgb, flat, p)
-    assert np.array_equal(o2[:, :w], o2[:, w:]) is False or True
-    assert o1.dtype == np.uint8 and o2.dtype == np.uint8
-    # row independence of everything except the vertical blurs: a frame whose rows are all equal stays row-constant
-    rgb_c = np.repeat(rgb[:1], h, axis=0)
-    d_c = np.repeat(depth[:1], h, axis=0)
-    oc = gen.process_frame(rgb_c, d_c, StereoParams(edge_softness=0.0))
-    assert (oc == oc[h // 2:h // 2 + 1]).all()
+    out = gen.process_frame(rgb, depth, StereoParams(**kw))
+    assert np.array_equal(out, gen.process_frame(rgb, depth, StereoParams(**kw))), 'not deterministic'
+    ref = O.process_frame(rgb, depth, O.Params(**kw))
+    diff = np.abs(out.astype(int) - ref.astype(int))
+    assert np.array_equal(out, ref), f'{(diff > 0).sum()} values differ, max {diff.max()}'
 
 
-def test_1080p_matches_oracle_on_a_band(gen):
-    """Full-width 1080p rows: the oracle on a 96-row band (cheap) must agree away from the band edges is not
-    valid because blurs are vertical; instead compare a genuinely small-height full-width frame."""
-    rgb, depth = make_pair(64, 1920, seed=5)
-    out = gen.process_frame(rgb, depth)
-    assert np.array_equal(out, O.process_frame(rgb, depth))
+def test_1080p_default_full_frame(gen):
+    """BASELINE.json configs[0]/[1]: one 1920x1080 frame, uint8 depth, default parameters."""
+    _compare_full(gen, 1080, 1920, np.uint8, {})
+
+
+def test_4k_u16_full_frame(gen):
+    """BASELINE.json configs[2]: 3840x2160, 16-bit depth, full-width SBS output."""
+    _compare_full(gen, 2160, 3840, np.uint16, {})
+
+
+def test_8k_band_aggressive(gen):
+    """BASELINE.json configs[4] geometry (7680 wide, md=100, conv=-50, smoothing 5) on a 256-row band so
+    that the oracle stays cheap; stretched_w must be 7929."""
+    kw = dict(max_disparity=100.0, convergence=-50.0, super_sampling=1.0, edge_softness=0.0, depth_gamma=1.0,
+              artifact_smoothing=5.0)
+    assert _lib.geometry(3840, 7680, StereoParams(**kw)).stretched_w == 7929
+    _compare_full(gen, 256, 7680, np.uint16, kw)
+    kw['super_sampling'] = 2.0
+    _compare_full(gen, 128, 7680, np.uint16, kw)

@@ -194,21 +194,23 @@ def test_inpaint_bit_exact(ctx, name):
     assert np.array_equal(out, ref), f'{(out != ref).any(axis=2).sum()} px differ'
 
 
-def test_inpaint_const_image_double_rounding(ctx):
-    """const-101 image with a 1-px hole inpaints to 102 (the +0.5 and the rounding both apply)."""
+def test_inpaint_const_image(ctx):
+    """Constant image: the ill-conditioned unit-gradient term makes every ulp count."""
     img = np.full((20, 20, 3), 101, np.uint8)
     valid = np.ones((20, 20), np.uint8)
     valid[10, 10] = 0
     out, ref = _inpaint_case(ctx, img, valid)
-    assert np.array_equal(out, ref) and out[10, 10, 0] == 102
+    assert np.array_equal(out, ref)
+    assert set(np.unique(out[9:12, 9:12])) <= {100, 101, 102}
 
 
 def test_inpaint_crop_culling_keeps_window_exact(ctx):
-    """Clusters that do not reach the kept columns may be skipped; kept columns must still be exact."""
+    """Clusters that do not reach the kept columns are skipped; the kept columns must still be exact."""
     h, w = 160, 400
     img = make_rgb(h, w, seed=9)
     rng = np.random.default_rng(3)
-    hole = rng.random((h, w)) < 0.003
+    hole = np.zeros((h, w), bool)
+    hole[:, 100:300] = rng.random((h, 200)) < 0.003
     hole[:, :30] = True
     hole[:, -18:] = True
     valid = (~hole).astype(np.uint8)
@@ -217,6 +219,7 @@ def test_inpaint_crop_culling_keeps_window_exact(ctx):
     out, ref = _inpaint_case(ctx, img, valid, keep=(k0, kw))
     assert np.array_equal(out[:, k0:k0 + kw], ref[:, k0:k0 + kw])
     assert not np.array_equal(out[:, :20], ref[:, :20])      # the far band was really skipped
+    assert (out[:, :20] == 0).all()
 
 
 def test_inpaint_real_warp_masks(ctx):

@@ -238,7 +238,7 @@ struct Slot {
     DevBuf in_rgb, in_depth, out_sbs;
     // intermediates
     DevBuf rgb_st, depth_st, depth_ss, viewA[2], viewB[2], vmask[2];
-    DevBuf st[2], tt[2], tile_u8[2], tile_i32[2], qkey[2], qidx[2];
+    DevBuf st[2], tt[2], pstate[2], tile_u8[2], tile_i32[2], qkey[2], qidx[2];
     DevBuf tabs;        // lanczos + axis tables
     DevBuf scalars;     // FrameScalars
     FrameScalars* h_scalars = nullptr;   // pinned mirror
@@ -254,10 +254,18 @@ struct Slot {
     int l_dtype = 0, l_H = 0, l_W = 0; vsc_params l_p; uint8_t* l_host_out = nullptr; size_t l_out_bytes = 0;
     int launches = 0;
     float last_ms = 0.f;
+    // optional per-kernel profiling (vsc_set_profiling): event pairs around every launch
+    std::vector<cudaEvent_t> pev;
+    std::vector<const char*> pname;
+    int pcount = 0;
 };
 
 struct vsc_ctx {
     int device = 0;
+    bool profiling = false;
+    cudaStream_t tstream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::vector<cudaEvent_t> tslot;
     int sm_count = 148;
     std::vector<Slot> slots;
     DevBuf color_w;     // bilateral colour LUT for sigmaColor = 30 (stereo_core.py:410)
@@ -335,7 +343,7 @@ extern "C" void vsc_destroy(vsc_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& s : ctx->slots) {
         DevBuf* bufs[] = {&s.in_rgb, &s.in_depth, &s.out_sbs, &s.rgb_st, &s.depth_st, &s.depth_ss, &s.viewA[0], &s.viewA[1],
-                          &s.viewB[0], &s.viewB[1], &s.vmask[0], &s.vmask[1], &s.st[0], &s.st[1], &s.tt[0], &s.tt[1],
+                          &s.viewB[0], &s.viewB[1], &s.vmask[0], &s.vmask[1], &s.st[0], &s.st[1], &s.tt[0], &s.tt[1], &s.pstate[0], &s.pstate[1],
                           &s.tile_u8[0], &s.tile_u8[1], &s.tile_i32[0], &s.tile_i32[1], &s.qkey[0], &s.qkey[1],
                           &s.qidx[0], &s.qidx[1], &s.tabs, &s.scalars};
         for (DevBuf* b : bufs) b->release();
@@ -393,13 +401,27 @@ static int ensure_tables(Slot& s, const vsc_geom& g) {
     return VSC_OK;
 }
 
-#define KCHECK(s) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(VSC_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); (s).launches++; } while (0)
+static bool g_profiling = false;   // mirrors ctx->profiling for the launch helpers
+static void prof_begin(Slot& s, const char* name) {
+    if (!g_profiling) return;
+    while ((int)s.pev.size() < 2 * (s.pcount + 1)) { cudaEvent_t e; cudaEventCreate(&e); s.pev.push_back(e); }
+    if ((int)s.pname.size() <= s.pcount) s.pname.resize(s.pcount + 1);
+    s.pname[s.pcount] = name;
+    cudaEventRecord(s.pev[2 * s.pcount], s.stream);
+}
+static void prof_end(Slot& s) {
+    if (!g_profiling) return;
+    cudaEventRecord(s.pev[2 * s.pcount + 1], s.stream);
+    s.pcount++;
+}
+#define KCHECK(s) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(VSC_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); (s).launches++; prof_end(s); } while (0)
 
 // ---- device-level stage launchers (all asynchronous on s.stream) --------------------------------
 static int run_lanczos_rgb(Slot& s, const uint8_t* d_rgb, int H, int W, int SW, uint8_t* d_out) {
     const int stage = (int)align_up((size_t)W * 3 + 16, 16);
     const size_t smem = stage + align_up((size_t)SW * 3 + 16, 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "frame width %d too large for the row-staged Lanczos kernel", W);
+    prof_begin(s, "lanczos_rgb_kernel");
     lanczos_rgb_kernel<<<H, kThreads, smem, s.stream>>>(d_rgb, W, SW, s.d_sx0, s.d_it, s.ib3, d_out, stage);
     KCHECK(s);
     return VSC_OK;
@@ -408,6 +430,7 @@ static int run_lanczos_depth(Slot& s, const void* d_depth, int dtype, int H, int
     const size_t smem = align_up((size_t)W * depth_elem(dtype) + 32, 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "frame width %d too large for the row-staged Lanczos kernel", W);
     FrameScalars* fs = s.scalars.as<FrameScalars>();
+    prof_begin(s, "lanczos_depth_kernel");
     if (dtype == VSC_DEPTH_U8)
         lanczos_depth_kernel<uint8_t><<<H, kThreads, smem, s.stream>>>((const uint8_t*)d_depth, W, SW, s.d_sx0, s.d_it, s.d_ft, s.ib3, s.beta3, d_out, fs);
     else if (dtype == VSC_DEPTH_U16)
@@ -419,6 +442,7 @@ static int run_lanczos_depth(Slot& s, const void* d_depth, int dtype, int H, int
 }
 static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_params& p, float* d_depth_st, float* d_depth_ss) {
     const size_t n = (size_t)g.height * g.stretched_w;
+    prof_begin(s, "normalize_kernel");
     normalize_kernel<<<ctx->sm_count * 4, kThreads, 0, s.stream>>>(d_depth_st, n, s.scalars.as<FrameScalars>());
     KCHECK(s);
     const int apply_gamma = p.depth_gamma != 1.0;
@@ -428,10 +452,12 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
         const int r = g.blur_k / 2, AH = DF_T + 2 * r;
         const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4;
         dim3 grid((g.ss_w + DF_T - 1) / DF_T, (g.ss_h + DF_T - 1) / DF_T);
+        prof_begin(s, "depth_front_kernel");
         depth_front_kernel<<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
                                                                g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
     } else {
         dim3 grid((g.ss_w + kThreads * 4 - 1) / (kThreads * 4), g.ss_h);
+        prof_begin(s, "depth_point_kernel");
         depth_point_kernel<<<grid, kThreads, 0, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
                                                             g.super_sampled, gamma, apply_gamma, d_depth_ss);
     }
@@ -456,6 +482,7 @@ static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint
     a.rgb_stage_bytes = (int)align_up((size_t)((int)(nsrc * ratio) + 8) * 3 + 32, 16);
     const size_t smem = (size_t)4 * a.TS * 4 + 2 * ((size_t)a.TS * 4 + 16) + 2 * (size_t)a.rgb_stage_bytes;
     dim3 grid(nseg, g.ss_h);
+    prof_begin(s, "warp_kernel");
     warp_kernel<<<grid, kThreads, smem, s.stream>>>(a);
     KCHECK(s);
     return VSC_OK;
@@ -473,6 +500,7 @@ static int run_bilateral(vsc_ctx* ctx, Slot& s, int Hs, int Ws, double smoothing
     const int TW = 32 + 2 * a.taps.radius;
     const size_t smem = (768 + (size_t)TW * TW) * 4;
     dim3 grid((Ws + 31) / 32, (Hs + 31) / 32, nviews), block(32, 8);
+    prof_begin(s, "bilateral_kernel");
     bilateral_kernel<<<grid, block, smem, s.stream>>>(a);
     KCHECK(s);
     return VSC_OK;
@@ -487,10 +515,11 @@ static int ensure_telea(Slot& s, int Hs, int Ws, int nviews) {
         int rc = 0;
         rc |= s.st[v].ensure(npx);
         rc |= s.tt[v].ensure(npx * 4);
+        rc |= s.pstate[v].ensure(npx * 4);
         rc |= s.tile_u8[v].ensure(nt * 2);
         rc |= s.tile_i32[v].ensure(nt * 4 * 11);
-        rc |= s.qkey[v].ensure(s.qcap * 8 * 2);
-        rc |= s.qidx[v].ensure(s.qcap * 4 * 2);
+        rc |= s.qkey[v].ensure(s.qcap * 8 * 3);
+        rc |= s.qidx[v].ensure(s.qcap * 4 * 3);
         if (rc) return VSC_E_NOMEM;
     }
     return VSC_OK;
@@ -518,21 +547,30 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
         V.lab = ib; V.csize = ib + nt; V.ctiles = ib + 2 * nt; V.cneed = ib + 3 * nt; V.cslot = ib + 4 * nt;
         V.cl_qoff = ib + 5 * nt; V.cl_toff = ib + 6 * nt; V.cl_ntiles = ib + 7 * nt; V.cl_size = ib + 8 * nt;
         V.cl_fill = ib + 9 * nt; V.tile_list = ib + 10 * nt;
-        V.qkey[0] = s.qkey[b].as<unsigned long long>(); V.qkey[1] = V.qkey[0] + s.qcap;
-        V.qidx[0] = s.qidx[b].as<unsigned>(); V.qidx[1] = V.qidx[0] + s.qcap;
+        V.qkey[0] = s.qkey[b].as<unsigned long long>(); V.qkey[1] = V.qkey[0] + s.qcap; V.qkey[2] = V.qkey[1] + s.qcap;
+        V.qidx[0] = s.qidx[b].as<unsigned>(); V.qidx[1] = V.qidx[0] + s.qcap; V.qidx[2] = V.qidx[1] + s.qcap;
+        V.pstate = s.pstate[b].as<unsigned>();
         V.qcap = (int)s.qcap;
     }
+    for (int v = 0; v < nviews; v++) CU(cudaMemsetAsync(s.pstate[v].p, 0x01, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'done'
     dim3 pgrid((Ws + 31) / 32, (Hs + 31) / 32, nviews), pblock(32, 8);
+    prof_begin(s, "telea_prepare_kernel");
     telea_prepare_kernel<<<pgrid, pblock, 0, s.stream>>>(a);
     KCHECK(s);
     const int tb = (int)((nt + kThreads - 1) / kThreads);
     const int tgrid = tb < ctx->sm_count * 8 ? tb : ctx->sm_count * 8;
+    prof_begin(s, "telea_ccl_init_kernel");
     telea_ccl_init_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);    KCHECK(s);
+    prof_begin(s, "telea_ccl_merge_kernel");
     telea_ccl_merge_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);   KCHECK(s);
+    prof_begin(s, "telea_ccl_flatten_kernel");
     telea_ccl_flatten_kernel<<<tgrid, kThreads, 0, s.stream>>>(a); KCHECK(s);
+    prof_begin(s, "telea_cluster_alloc_kernel");
     telea_cluster_alloc_kernel<<<tgrid, kThreads, 0, s.stream>>>(a); KCHECK(s);
+    prof_begin(s, "telea_cluster_fill_kernel");
     telea_cluster_fill_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);  KCHECK(s);
-    dim3 cgrid(ctx->sm_count * 2, nviews);
+    dim3 cgrid(ctx->sm_count * 2, nviews);   // persistent CTAs pulling clusters from a queue
+    prof_begin(s, "telea_cluster_kernel");
     telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
     KCHECK(s);
     return VSC_OK;
@@ -551,6 +589,7 @@ static int run_backend(Slot& s, const vsc_geom& g, double sharpen, const uchar4*
                         (size_t)BE_OY * (BE_OX * 3 + 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "super_sampling too large for the back-end tile (%zu bytes of shared memory)", smem);
     dim3 grid((g.width + BE_OX - 1) / BE_OX, (g.height + BE_OY - 1) / BE_OY, 2);
+    prof_begin(s, "backend_kernel");
     backend_kernel<<<grid, kThreads, smem, s.stream>>>(a);
     KCHECK(s);
     return VSC_OK;
@@ -580,7 +619,9 @@ static int enqueue_frame(vsc_ctx* ctx, Slot& s, const uint8_t* d_rgb, const void
     rc = ensure_tables(s, g);
     if (rc) return rc;
     s.launches = 0;
+    s.pcount = 0;
     CU(cudaEventRecord(s.ev0, s.stream));
+    prof_begin(s, "frame_init_kernel");
     frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
     KCHECK(s);
     if ((rc = run_lanczos_rgb(s, d_rgb, g.height, g.width, g.stretched_w, s.rgb_st.as<uint8_t>()))) return rc;
@@ -972,5 +1013,54 @@ extern "C" int vsc_debug_fetch(vsc_ctx* ctx, int which, void* dst, size_t bytes)
     DevBuf* b[] = {&s.rgb_st, &s.depth_st, &s.depth_ss, &s.viewA[0], &s.viewA[1], &s.viewB[0], &s.viewB[1], &s.vmask[0], &s.vmask[1]};
     if (which < 0 || which > 8 || !b[which]->p || b[which]->cap < bytes) return fail(VSC_E_INVALID, "bad buffer id or size");
     CU(cudaMemcpy(dst, b[which]->p, bytes, cudaMemcpyDeviceToHost));
+    return VSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int vsc_set_profiling(vsc_ctx* ctx, int on) {
+    if (!ctx) return fail(VSC_E_INVALID, "null context");
+    ctx->profiling = on != 0;
+    g_profiling = ctx->profiling;
+    return VSC_OK;
+}
+// per-kernel device times of the last completed frame on `slot` (needs vsc_set_profiling(ctx,1) before submit)
+extern "C" int vsc_slot_kernel_times(vsc_ctx* ctx, int slot, int max_n, const char** names, float* ms) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad argument");
+    Slot& s = ctx->slots[slot];
+    int n = s.pcount < max_n ? s.pcount : max_n;
+    for (int i = 0; i < n; i++) {
+        names[i] = s.pname[i];
+        if (cudaEventElapsedTime(&ms[i], s.pev[2 * i], s.pev[2 * i + 1]) != cudaSuccess) ms[i] = -1.f;
+    }
+    return n;
+}
+// device-side timer spanning all slot streams: begin makes every slot stream wait on a start event,
+// end records after every slot stream has drained; elapsed is measured between the two events.
+extern "C" int vsc_timer_begin(vsc_ctx* ctx) {
+    if (!ctx) return fail(VSC_E_INVALID, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->tstream) {
+        CU(cudaStreamCreateWithFlags(&ctx->tstream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ctx->t0)); CU(cudaEventCreate(&ctx->t1));
+        ctx->tslot.resize(ctx->slots.size());
+        for (auto& e : ctx->tslot) CU(cudaEventCreate(&e));
+    }
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(ctx->t0, ctx->tstream));
+    for (auto& s : ctx->slots) CU(cudaStreamWaitEvent(s.stream, ctx->t0, 0));
+    return VSC_OK;
+}
+extern "C" int vsc_timer_end(vsc_ctx* ctx, float* ms) {
+    if (!ctx || !ms || !ctx->tstream) return fail(VSC_E_INVALID, "timer not started");
+    CU(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < ctx->slots.size(); i++) {
+        CU(cudaEventRecord(ctx->tslot[i], ctx->slots[i].stream));
+        CU(cudaStreamWaitEvent(ctx->tstream, ctx->tslot[i], 0));
+    }
+    CU(cudaEventRecord(ctx->t1, ctx->tstream));
+    CU(cudaEventSynchronize(ctx->t1));
+    CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
     return VSC_OK;
 }

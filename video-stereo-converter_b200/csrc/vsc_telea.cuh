@@ -47,8 +47,9 @@ struct TeleaView {
     // clusters
     int* cl_qoff;  int* cl_toff;  int* cl_ntiles;  int* cl_size;  int* cl_fill;
     int* tile_list;            // [ntiles_active]
-    unsigned long long* qkey[2];   // pool / current generation keys
-    unsigned* qidx[2];
+    unsigned long long* qkey[3];   // two ping-pong pools + the current generation
+    unsigned* qidx[3];
+    unsigned* pstate;          // [Hs][Ws] (global pop index << 1) | done, for the dataflow order
     int qcap;
 };
 
@@ -189,7 +190,9 @@ __global__ void telea_cluster_alloc_kernel(const __grid_constant__ TeleaArgs a) 
         const TeleaView& V = a.v[v];
         for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
             if (V.lab[t] != t || !V.cneed[t]) continue;
-            const int ci = atomicAdd(&a.fs->ncl[v], 1);
+            // big clusters get slots from the front, small ones from the back: the work queue starts the
+            // long poles first
+            const int ci = V.csize[t] >= 1024 ? atomicAdd(&a.fs->nbig[v], 1) : n - 1 - atomicAdd(&a.fs->nsmall[v], 1);
             V.cl_qoff[ci] = atomicAdd(&a.fs->qbump[v], V.csize[t]);
             V.cl_toff[ci] = atomicAdd(&a.fs->tbump[v], V.ctiles[t]);
             V.cl_ntiles[ci] = V.ctiles[t];
@@ -345,9 +348,7 @@ struct Marcher {
     }
 };
 
-// warp-wide bitonic sort of n (key,idx) pairs in global memory, ascending by key.  All compare-exchanges are
-// ascending (the "flip" formulation), so the virtual +inf padding above n never has to move and pairs whose
-// partner is >= n can simply be skipped.
+// ---- CTA-wide helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ void cmpswap(unsigned long long* key, unsigned* idx, int i, int p) {
     const unsigned long long a = key[i], b = key[p];
     if (a > b) {
@@ -355,35 +356,68 @@ __device__ __forceinline__ void cmpswap(unsigned long long* key, unsigned* idx, 
         const unsigned t = idx[i]; idx[i] = idx[p]; idx[p] = t;
     }
 }
-__device__ void warp_sort(unsigned long long* key, unsigned* idx, int n, int lane) {
+// CTA-wide bitonic sort of n (key,idx) pairs in global memory, ascending by key.  All compare-exchanges
+// are ascending (the "flip" formulation), so the virtual +inf padding above n never has to move and pairs
+// whose partner is >= n are simply skipped.
+__device__ void block_sort(unsigned long long* key, unsigned* idx, int n) {
     if (n <= 1) return;
     int N = 1;
     while (N < n) N <<= 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
     for (int k = 2; k <= N; k <<= 1) {
-        for (int i = lane; i < n; i += 32) {
+        for (int i = tid; i < n; i += nt) {
             const int p = i ^ (k - 1);
             if (p > i && p < n) cmpswap(key, idx, i, p);
         }
-        __syncwarp();
+        __syncthreads();
         for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = lane; i < n; i += 32) {
+            for (int i = tid; i < n; i += nt) {
                 const int p = i ^ j;
                 if (p > i && p < n) cmpswap(key, idx, i, p);
             }
-            __syncwarp();
+            __syncthreads();
         }
     }
 }
 
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int TELEA_WARPS = 16;
+constexpr int TELEA_DC = 6;   // two pops closer than this (Chebyshev) are ordered; farther apart they commute
+
+struct MarchShared {
+    int npool, npool2, ncur, next_e, gbase;
+    unsigned tmin;
+    int ci;
+    float taps[TELEA_WARPS][28 * 10];
+};
+
+// One fast-marching pass over one cluster, executed by a whole CTA.
+//  * the queue is processed in generations (see file header); each generation is sorted CTA-wide
+//  * inside a generation the pops are executed as a dataflow: warps claim pops in sorted order and a pop
+//    starts once every earlier pop within TELEA_DC pixels has finished (pstate: (global pop index << 1) |
+//    done).  A pop touches pixels within 5 of its own position and writes within 1, so pops farther apart
+//    than 6 commute and the result is identical to the sequential order.
+//  * the FIFO tie-break of the reference's queue is (global pop index, neighbour q), which is exactly the
+//    order in which a sequential run would have pushed.
 template <bool OUTER>
-__device__ void march(const Marcher& mc, const TeleaView& V, int qoff, int ntiles, const int* tiles, int tw,
-                      float* sm, int lane) {
-    unsigned long long* pool_k = V.qkey[0] + qoff;  unsigned* pool_i = V.qidx[0] + qoff;
-    unsigned long long* cur_k = V.qkey[1] + qoff;   unsigned* cur_i = V.qidx[1] + qoff;
-    const int Ws = mc.Ws, Hs = mc.Hs;
-    int npool = 0;
-    // initial queue: the band pixels (T = 0) in raster order == ascending linear index
-    for (int ti = 0; ti < ntiles; ti++) {
+__device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw) {
+    unsigned long long* pk[2] = {V.qkey[0] + qoff, V.qkey[1] + qoff};
+    unsigned* pi[2] = {V.qidx[0] + qoff, V.qidx[1] + qoff};
+    unsigned long long* cur_k = V.qkey[2] + qoff;
+    unsigned* cur_i = V.qidx[2] + qoff;
+    const int Ws = mc.Ws, Hs = mc.Hs, lane = mc.lane, wid = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.next_e = 0; sh.gbase = 1; sh.tmin = 0xffffffffu; }
+    __syncthreads();
+    // initial queue: the band pixels, T = 0, ordered by raster position (= linear index in the key)
+    for (int ti = wid; ti < ntiles; ti += TELEA_WARPS) {
         const int t = tiles[ti];
         const int ty = t / tw, tx = t - ty * tw;
 #pragma unroll
@@ -393,41 +427,81 @@ __device__ void march(const Marcher& mc, const TeleaView& V, int qoff, int ntile
             unsigned p = 0;
             if (y < Hs && x < Ws) { p = (unsigned)y * (unsigned)Ws + (unsigned)x; isb = (V.st[p] & ST_BAND0) != 0; }
             const unsigned bm = __ballot_sync(0xffffffffu, isb);
+            int base = 0;
+            if (lane == 0 && bm) base = atomicAdd(&sh.npool, __popc(bm));
+            base = __shfl_sync(0xffffffffu, base, 0);
             if (isb) {
-                const int pos = npool + __popc(bm & ((1u << lane) - 1));
-                pool_k[pos] = (unsigned long long)p;   // T bits = 0
-                pool_i[pos] = p;
+                const int pos = base + __popc(bm & ((1u << lane) - 1));
+                pk[0][pos] = (unsigned long long)p;
+                pi[0][pos] = p;
             }
-            npool += __popc(bm);
         }
     }
-    __syncwarp();
-    unsigned seq = 0;
-    while (npool > 0) {
+    __syncthreads();
+    int src = 0;
+    while (true) {
+        const int npool = sh.npool;
+        if (npool == 0) break;
+        unsigned long long* pool_k = pk[src]; unsigned* pool_i = pi[src];
+        unsigned long long* next_k = pk[src ^ 1]; unsigned* next_i = pi[src ^ 1];
         // generation = entries with T < Tmin + 0.7
         unsigned tmin = 0xffffffffu;
-        for (int i = lane; i < npool; i += 32) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
+        for (int i = tid; i < npool; i += nt) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
         tmin = __reduce_min_sync(0xffffffffu, tmin);
-        const float thr = __uint_as_float(tmin) + 0.7f;
-        int ncur = 0, nkeep = 0;
-        for (int base = 0; base < npool; base += 32) {
-            const int i = base + lane;
-            unsigned long long k = 0; unsigned p = 0;
-            bool have = i < npool, sel = false;
-            if (have) { k = pool_k[i]; p = pool_i[i]; sel = __uint_as_float((unsigned)(k >> 32)) < thr; }
-            const unsigned ms = __ballot_sync(0xffffffffu, have && sel), mk = __ballot_sync(0xffffffffu, have && !sel);
-            __syncwarp();
-            if (have && sel) { const int pos = ncur + __popc(ms & ((1u << lane) - 1)); cur_k[pos] = k; cur_i[pos] = p; }
-            if (have && !sel) { const int pos = nkeep + __popc(mk & ((1u << lane) - 1)); pool_k[pos] = k; pool_i[pos] = p; }
-            ncur += __popc(ms); nkeep += __popc(mk);
-            __syncwarp();
+        if (lane == 0) atomicMin(&sh.tmin, tmin);
+        __syncthreads();
+        const float thr = __uint_as_float(sh.tmin) + 0.7f;
+        for (int i = tid; i < npool; i += nt) {
+            const unsigned long long k = pool_k[i];
+            const unsigned p = pool_i[i];
+            if (__uint_as_float((unsigned)(k >> 32)) < thr) {
+                const int pos = atomicAdd(&sh.ncur, 1);
+                cur_k[pos] = k; cur_i[pos] = p;
+            } else {
+                const int pos = atomicAdd(&sh.npool2, 1);
+                next_k[pos] = k; next_i[pos] = p;
+            }
         }
-        npool = nkeep;
-        warp_sort(cur_k, cur_i, ncur, lane);
-        __syncwarp();
-        for (int e = 0; e < ncur; e++) {
+        __syncthreads();
+        const int ncur = sh.ncur, gbase = sh.gbase;
+        block_sort(cur_k, cur_i, ncur);
+        __syncthreads();
+        for (int e = tid; e < ncur; e += nt) V.pstate[cur_i[e]] = (unsigned)(gbase + e) << 1;
+        __syncthreads();
+        // dataflow over the sorted generation
+        while (true) {
+            int e = 0;
+            if (lane == 0) e = atomicAdd(&sh.next_e, 1);
+            e = __shfl_sync(0xffffffffu, e, 0);
+            if (e >= ncur) break;
             const unsigned p = cur_i[e];
+            const unsigned G = (unsigned)(gbase + e);
             const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
+            // wait for every earlier pop within TELEA_DC
+            {
+                constexpr int D = 2 * TELEA_DC + 1;
+                bool pend[(D * D + 31) / 32];
+#pragma unroll
+                for (int r = 0; r < (D * D + 31) / 32; r++) {
+                    const int idx = lane + 32 * r;
+                    const int dy = idx / D - TELEA_DC, dx = idx % D - TELEA_DC;
+                    pend[r] = idx < D * D && mc.inb(yy + dy, xx + dx);
+                }
+                while (true) {
+                    bool any = false;
+#pragma unroll
+                    for (int r = 0; r < (D * D + 31) / 32; r++) {
+                        if (!pend[r]) continue;
+                        const int idx = lane + 32 * r;
+                        const int dy = idx / D - TELEA_DC, dx = idx % D - TELEA_DC;
+                        const unsigned v = ld_acquire(&V.pstate[(size_t)(yy + dy) * Ws + xx + dx]);
+                        pend[r] = (v >> 1) < G && !(v & 1u);
+                        any |= pend[r];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) break;
+                }
+                __syncwarp();
+            }
             if (OUTER && lane == 0) V.st[p] = (V.st[p] & ~O_MASK) | O_CHANGE;
             __syncwarp();
 #pragma unroll 1
@@ -439,43 +513,51 @@ __device__ void march(const Marcher& mc, const TeleaView& V, int qoff, int ntile
                 const float dist = mc.min4<OUTER>(y, x);
                 if (lane == 0) V.tt[pn] = dist;
                 __syncwarp();
-                if (!OUTER) mc.inpaint(y, x, dist, sm);
+                if (!OUTER) mc.inpaint(y, x, dist, sh.taps[wid]);
                 if (lane == 0) {
                     const unsigned char s = V.st[pn];
                     V.st[pn] = OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND);
-                    pool_k[npool] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)seq;
-                    pool_i[npool] = (unsigned)pn;
+                    const int pos = atomicAdd(&sh.npool2, 1);
+                    next_k[pos] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(G * 4u + (unsigned)q);
+                    next_i[pos] = (unsigned)pn;
                 }
-                npool++; seq++;
                 __syncwarp();
             }
+            if (lane == 0) st_release(&V.pstate[p], (G << 1) | 1u);
         }
+        __syncthreads();
+        if (tid == 0) {
+            sh.gbase = gbase + ncur; sh.npool = sh.npool2; sh.npool2 = 0; sh.ncur = 0; sh.next_e = 0; sh.tmin = 0xffffffffu;
+        }
+        src ^= 1;
+        __syncthreads();
     }
 }
 
-constexpr int TELEA_WARPS = 4;
 __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
-    __shared__ float sm_all[TELEA_WARPS][28 * 10];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ MarchShared sh;
+    const int lane = threadIdx.x & 31;
     const int v = blockIdx.y;
     const TeleaView& V = a.v[v];
-    const int ncl = a.fs->ncl[v];
+    const int nbig = a.fs->nbig[v], ncl = nbig + a.fs->nsmall[v];
     if (a.fs->qbump[v] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&a.fs->overflow, a.fs->qbump[v]);
         return;
     }
     Marcher mc{V, a.Hs, a.Ws, lane};
+    const int cap = a.tw * a.th;
     while (true) {
-        int ci = 0;
-        if (lane == 0) ci = atomicAdd(&a.fs->next[v], 1);
-        ci = __shfl_sync(0xffffffffu, ci, 0);
-        if (ci >= ncl) break;
+        if (threadIdx.x == 0) sh.ci = atomicAdd(&a.fs->next[v], 1);
+        __syncthreads();
+        const int i = sh.ci;
+        if (i >= ncl) break;
+        const int ci = i < nbig ? i : cap - 1 - (i - nbig);     // big clusters are queued first
         const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
         const int* tiles = V.tile_list + V.cl_toff[ci];
-        march<true>(mc, V, qoff, ntiles, tiles, a.tw, sm_all[wid], lane);
-        __syncwarp();
-        march<false>(mc, V, qoff, ntiles, tiles, a.tw, sm_all[wid], lane);
-        __syncwarp();
+        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw);
+        __syncthreads();
+        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw);
+        __syncthreads();
     }
 }
 

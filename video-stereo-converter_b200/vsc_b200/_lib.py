@@ -19,6 +19,8 @@ EXPORTS = [
     'vsc_wait', 'vsc_submit_device', 'vsc_sync', 'vsc_slot_stream', 'vsc_slot_elapsed_ms', 'vsc_slot_launches',
     'vsc_stage_lanczos', 'vsc_stage_depth', 'vsc_stage_warp', 'vsc_stage_bilateral', 'vsc_stage_inpaint',
     'vsc_stage_backend', 'vsc_stage_warp_f32', 'vsc_stage_normalize_f32', 'vsc_stage_gamma_f32',
+    'vsc_set_profiling', 'vsc_slot_kernel_times', 'vsc_timer_begin', 'vsc_timer_end', 'vsc_debug_fetch',
+    'vsc_debug_telea_state',
 ]
 
 
@@ -86,6 +88,12 @@ def load():
     lib.vsc_stage_warp_f32.argtypes = [vp, vp, vp, i, i, i, d, vp, vp, vp, vp]
     lib.vsc_stage_normalize_f32.argtypes = [vp, vp, C.c_size_t, vp]
     lib.vsc_stage_gamma_f32.argtypes = [vp, vp, C.c_size_t, d, vp]
+    lib.vsc_set_profiling.argtypes = [vp, i]
+    lib.vsc_slot_kernel_times.argtypes = [vp, i, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    lib.vsc_timer_begin.argtypes = [vp]
+    lib.vsc_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.vsc_debug_fetch.argtypes = [vp, i, vp, C.c_size_t]
+    lib.vsc_debug_telea_state.argtypes = [vp, i, vp, vp, C.c_size_t]
     if lib.vsc_abi_version() != 1:
         raise ImportError('libvsc_b200.so ABI version mismatch')
     _lib = lib

@@ -181,38 +181,87 @@ class StereoGenerator:
         return out
 
     # -- asynchronous pipeline ---------------------------------------------------------------------
-    def submit(self, slot: int, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> None:
-        """Copy the frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
-        p = params or self._DEFAULT_PARAMS
-        if self._pending[slot] is not None:
-            raise RuntimeError(f'slot {slot} has an uncollected frame')
-        rgb_c, depth_c, code = self._check_inputs(rgb, depth)
-        h, w = rgb_c.shape[:2]
-        key = (h, w, depth_c.dtype.str)
+    def pinned_inputs(self, slot: int, h: int, w: int, depth_dtype=np.uint8):
+        """Page-locked (rgb[h,w,3], depth[h,w]) arrays of `slot` for a loader to decode into."""
+        key = (int(h), int(w), np.dtype(depth_dtype).str)
         pin = self._pinned[slot]
         if pin is None or pin[0] != key:
+            if self._pending[slot] is not None:
+                raise RuntimeError(f'slot {slot} has an uncollected frame')
             if pin is not None:
                 for b in pin[1:]:
                     b.free()
-            pin = (key, _lib.PinnedBuffer((h, w, 3), np.uint8), _lib.PinnedBuffer((h, w), depth_c.dtype),
+            pin = (key, _lib.PinnedBuffer((h, w, 3), np.uint8), _lib.PinnedBuffer((h, w), depth_dtype),
                    _lib.PinnedBuffer((h, 2 * w, 3), np.uint8))
             self._pinned[slot] = pin
-        np.copyto(pin[1].array, rgb_c)
-        np.copyto(pin[2].array, depth_c)
-        _lib.check(self._lib.vsc_submit(self._ctx.handle, slot, _lib.ptr(pin[1].array), _lib.ptr(pin[2].array), code, h, w,
-                                        C.byref(_lib.make_params(p)), _lib.ptr(pin[3].array)))
+        return pin[1].array, pin[2].array
+
+    def submit_pinned(self, slot: int, params: StereoParams | None = None) -> None:
+        """Enqueue H2D + kernels + D2H for the frame currently in the slot's pinned input arrays."""
+        p = params or self._DEFAULT_PARAMS
+        pin = self._pinned[slot]
+        if pin is None:
+            raise RuntimeError('call pinned_inputs(slot, h, w, dtype) first')
+        if self._pending[slot] is not None:
+            raise RuntimeError(f'slot {slot} has an uncollected frame')
+        h, w, _ = pin[0]
+        _lib.check(self._lib.vsc_submit(self._ctx.handle, slot, _lib.ptr(pin[1].array), _lib.ptr(pin[2].array),
+                                        _lib.depth_code(pin[2].array.dtype), h, w, C.byref(_lib.make_params(p)),
+                                        _lib.ptr(pin[3].array)))
         self._pending[slot] = (h, w)
 
-    def collect(self, slot: int) -> np.ndarray:
-        """Wait for the slot's frame and return a fresh array the caller owns (the reference hands
-        its result to another thread, sbs_generator.py:325, so it must not alias a reused buffer)."""
+    def submit(self, slot: int, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> None:
+        """Copy the frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
+        rgb_c, depth_c, _ = self._check_inputs(rgb, depth)
+        h, w = rgb_c.shape[:2]
+        prgb, pdepth = self.pinned_inputs(slot, h, w, depth_c.dtype)
+        np.copyto(prgb, rgb_c)
+        np.copyto(pdepth, depth_c)
+        self.submit_pinned(slot, params)
+
+    def collect(self, slot: int, copy: bool = True) -> np.ndarray:
+        """Wait for the slot's frame.  copy=True returns a fresh array the caller owns (the reference
+        hands its result to another thread, sbs_generator.py:325, so it must not alias a reused
+        buffer); copy=False returns the pinned output, valid until the slot is submitted again."""
         if self._pending[slot] is None:
             raise RuntimeError(f'slot {slot} has no frame in flight')
         try:
             _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
         finally:
             self._pending[slot] = None
-        return self._pinned[slot][3].array.copy()
+        out = self._pinned[slot][3].array
+        return out.copy() if copy else out
+
+    def submit_device(self, slot: int, d_rgb: int, d_depth: int, depth_dtype, h: int, w: int, d_out: int,
+                      params: StereoParams | None = None) -> None:
+        """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr()), no copies."""
+        p = params or self._DEFAULT_PARAMS
+        _lib.check(self._lib.vsc_submit_device(self._ctx.handle, slot, C.c_void_p(d_rgb), C.c_void_p(d_depth),
+                                               _lib.depth_code(depth_dtype), h, w, C.byref(_lib.make_params(p)),
+                                               C.c_void_p(d_out)))
+
+    def wait(self, slot: int) -> None:
+        _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
+
+    # -- measurement -------------------------------------------------------------------------------
+    def timer_begin(self) -> None:
+        _lib.check(self._lib.vsc_timer_begin(self._ctx.handle))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._lib.vsc_timer_end(self._ctx.handle, C.byref(ms)))
+        return float(ms.value)
+
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self._lib.vsc_set_profiling(self._ctx.handle, int(on)))
+
+    def kernel_times(self, slot: int = 0):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = self._lib.vsc_slot_kernel_times(self._ctx.handle, slot, 64, names, ms)
+        if n < 0:
+            _lib.check(n)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def process_batch(self, frames: Iterable[Tuple[np.ndarray, np.ndarray]],
                       params: StereoParams | None = None) -> List[np.ndarray]:
