@@ -158,6 +158,8 @@ int vsc_timer_end(vsc_ctx *ctx, float *ms);
 /* copies of slot 0's intermediates / Telea state after a completed call, for stage bisection in tests */
 int vsc_debug_fetch(vsc_ctx *ctx, int which, void *dst, size_t bytes);
 int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, size_t n);
+/* 64 phase counters of the hole-filling march (non-zero only in -DVSC_TELEA_STATS profiling builds) */
+int vsc_debug_telea_stats(vsc_ctx *ctx, unsigned long long *out64);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,90 @@
+"""CUDA path against the golden vectors of the UNMODIFIED reference (tests/golden), and the drop-in driver."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import ROOT
+from test_oracle_golden import GOLDEN, check_sbs_against_reference, load
+from vsc_b200 import StereoGenerator, StereoParams, _lib
+from vsc_b200.synthetic import make_pair
+
+pytestmark = pytest.mark.gpu
+PKG = os.path.join(ROOT, 'video-stereo-converter_b200')
+
+
+@pytest.fixture(scope='module')
+def gen():
+    g = StereoGenerator('cuda', n_slots=2)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(gen, path):
+    z, kw = load(path)
+    out = gen.process_frame(z['rgb'], z['depth'], StereoParams(**kw))
+    check_sbs_against_reference(out, z['sbs'], kw)
+    # hole masks / shift indices as the reference produced them: bit-exact (stage-wise, through the C ABI)
+    lib = _lib.load()
+    h, w = z['rgb'].shape[:2]
+    g = _lib.geometry(h, w, StereoParams(**kw))
+    taps = {}
+    O.process_frame(z['rgb'], z['depth'], O.Params(**kw), taps)
+    outs = [np.empty((g.ss_h, g.ss_w, 3), np.uint8), np.empty((g.ss_h, g.ss_w), np.uint8), np.empty((g.ss_h, g.ss_w, 3), np.uint8),
+            np.empty((g.ss_h, g.ss_w), np.uint8)]
+    depth_ss = np.ascontiguousarray(taps['depth_ss'])
+    _lib.check(lib.vsc_stage_warp(gen._ctx.handle, _lib.ptr(taps['rgb_stretched']), _lib.ptr(depth_ss), h, g.stretched_w, g.ss_h, g.ss_w,
+                                  float(kw.get('max_disparity', 50.0)), 0, *[_lib.ptr(o) for o in outs], None))
+    shape = tuple(z['mask_shape'])
+    for k, side in ((1, 'left'), (3, 'right')):
+        ref_mask = np.unpackbits(z['mask_' + side])[:shape[0] * shape[1]].reshape(shape)
+        assert np.array_equal(outs[k], ref_mask), side
+
+
+def _make_workflow(tmp_path, n, h=72, w=128):
+    import cv2
+    wf = tmp_path / 'wf'
+    for d in ('frames', 'depth_maps', 'sbs'):
+        (wf / d).mkdir(parents=True)
+    cfg = {'input_video': 'in.mkv', 'output_video': 'out.mkv',
+           'directories': {'frames': 'frames', 'depth_maps': 'depth_maps', 'sbs': 'sbs', 'chunks': 'chunks'},
+           'stereo': {'max_disparity': 50.0, 'convergence': -10.0, 'super_sampling': 3.0, 'edge_softness': 20.0,
+                      'artifact_smoothing': 1.0, 'depth_gamma': 0.2, 'sharpen': 14.0},
+           'depth': {'save_16bit': True}, 'encoding': {'crf': 19, 'preset': 'slow'},
+           'free_space': {'sbs_generator': 'none', 'chunk_generator': 'none'}}
+    (wf / 'config.json').write_text(json.dumps(cfg))
+    frames = []
+    for i in range(n):
+        rgb, depth = make_pair(h, w, seed=i, depth_dtype=np.uint16 if i % 2 else np.uint8)
+        cv2.imwrite(str(wf / 'frames' / f'frame_{i:06d}.png'), cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+        cv2.imwrite(str(wf / 'depth_maps' / (f'depth_frame_{i:06d}.tif' if i % 2 else f'depth_frame_{i:06d}.png')), depth)
+        frames.append((rgb, depth))
+    return wf, frames
+
+
+def test_sbs_generator_cli_end_to_end(tmp_path):
+    import cv2
+    n = 9
+    wf, frames = _make_workflow(tmp_path, n)
+    # frame 3 is already done: must be skipped, not rewritten (resume rule, sbs_generator.py:178-185)
+    (wf / 'sbs' / 'sbs_000003.png').write_bytes(b'sentinel')
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive', '--gpus', '1', '--slots', '3'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f'Found: {n} frame pairs, 1 already processed, {n - 1} to process' in r.stdout
+    assert (wf / 'sbs' / 'sbs_000003.png').read_bytes() == b'sentinel'
+    assert sorted(p.name for p in (wf / 'sbs').iterdir()) == [f'sbs_{i:06d}.png' for i in range(n)]
+    for i, (rgb, depth) in enumerate(frames):
+        if i == 3:
+            continue
+        got = cv2.cvtColor(cv2.imread(str(wf / 'sbs' / f'sbs_{i:06d}.png'), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        assert np.array_equal(got, O.process_frame(rgb, depth, O.Params())), i
+    # second run: nothing left
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive'], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'All frames already processed.' in r.stdout

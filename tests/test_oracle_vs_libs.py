@@ -1,0 +1,178 @@
+"""The oracle's restatements of third-party arithmetic against the libraries themselves (OpenCV and
+PyTorch are part of the image; the reference calls exactly these functions)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from vsc_b200.synthetic import make_depth, make_rgb
+
+cv2 = pytest.importorskip('cv2')
+torch = pytest.importorskip('torch')
+F = torch.nn.functional
+
+
+@pytest.mark.parametrize('h,w,dw', [(37, 160, 270), (12, 1920, 2030), (6, 3840, 3949), (11, 100, 137)])
+def test_lanczos4_bit_exact_vs_cv2(h, w, dw):
+    rng = np.random.default_rng(h)
+    for a in (rng.integers(0, 256, (h, w, 3), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8),
+              rng.integers(0, 65536, (h, w)).astype(np.uint16), rng.random((h, w), dtype=np.float32)):
+        ref = cv2.resize(a, (dw, h), interpolation=cv2.INTER_LANCZOS4)
+        assert np.array_equal(O.lanczos4_h(a, dw), ref), a.dtype
+
+
+@pytest.mark.parametrize('h,w,s', [(120, 270, 3.0), (108, 203, 2.5), (64, 99, 1.3)])
+def test_bilinear_bit_exact_vs_torch(h, w, s):
+    rng = np.random.default_rng(w)
+    x = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+    oh, ow = int(h * s), int(w * s)
+    ref = F.interpolate(torch.from_numpy(x)[None], size=(oh, ow), mode='bilinear', align_corners=False)[0].numpy()
+    assert np.array_equal(O.bilinear_up(x, oh, ow), ref)
+
+
+def _kornia_blur(x, k, sigma):
+    n = torch.arange(k, dtype=torch.float32) - (k // 2)
+    g = torch.exp(-(n * n) / (2.0 * float(sigma) ** 2))
+    g = g / g.sum()
+    c = x.shape[1]
+    x = F.conv2d(F.pad(x, (k // 2, k // 2, 0, 0), mode='reflect'), g.view(1, 1, 1, k).expand(c, 1, 1, k), groups=c)
+    x = F.conv2d(F.pad(x, (0, 0, k // 2, k // 2), mode='reflect'), g.view(1, 1, k, 1).expand(c, 1, k, 1), groups=c)
+    return x, g.numpy()
+
+
+@pytest.mark.parametrize('k,sigma,c', [(31, 20.0, 1), (5, 1.0, 3), (13, 2.2, 1)])
+def test_gaussian_blur_vs_torch_conv(k, sigma, c):
+    rng = np.random.default_rng(k)
+    x = rng.random((c, 90, 130), dtype=np.float32) * 255
+    ref, taps = _kornia_blur(torch.from_numpy(x)[None], k, sigma)
+    assert np.array_equal(O.gauss_taps(k, sigma), taps)
+    # conv2d's summation order is backend- and shape-dependent (A.4): a couple of ulp, never more
+    mine = O.gauss_blur(x, k, sigma)
+    r = ref[0].numpy()
+    assert np.abs(mine - r).max() <= 1e-6 * np.abs(r).max() * 4
+
+
+def test_gauss_taps_match_torch_for_most_slider_values():
+    bad = 0
+    for es in np.arange(0.5, 30.5, 0.5):
+        k = O.soft_kernel_size(float(es))
+        n = torch.arange(k, dtype=torch.float32) - (k // 2)
+        g = torch.exp(-(n * n) / (2.0 * float(es) ** 2))
+        bad += not np.array_equal((g / g.sum()).numpy(), O.gauss_taps(k, float(es)))
+    assert bad <= 6      # torch's vectorised expf differs from the correctly rounded exp for a few sigmas (<= 1 ulp)
+
+
+def test_sharpen_and_area_pool_bit_exact_vs_torch():
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 256, (3, 120, 150)).astype(np.float32)
+    xt = torch.from_numpy(x)[None]
+    blur, _ = _kornia_blur(xt, 5, 1.0)
+    ref = (xt + 14.0 * (xt - blur)).clamp(0, 255)
+    mine = O.sharpen(x, 14.0)
+    assert np.abs(mine - ref[0].numpy()).max() <= 2e-3      # 15x amplification of the blur's last ulp
+    refn = np.ascontiguousarray(ref[0].numpy())
+    for oh, ow in ((40, 50), (48, 60), (100, 111)):
+        r = F.interpolate(ref, size=(oh, ow), mode='area')[0].numpy()
+        assert np.array_equal(O.area_pool(refn, oh, ow), r)
+
+
+@pytest.mark.parametrize('g', [0.1, 0.2, 0.55, 1.5, 2.0])
+def test_gamma_within_one_ulp_of_torch(g):
+    rng = np.random.default_rng(0)
+    d = rng.random(200000, dtype=np.float32)
+    ref = torch.pow(torch.from_numpy(d).clamp(0.001, 1.0), g).numpy()
+    mine = O.apply_gamma(d, g)
+    assert np.abs(ref.view(np.int32) - mine.view(np.int32)).max() <= 1
+    exact = np.power(np.clip(d, np.float32(0.001), 1).astype(np.float64), float(np.float32(g))).astype(np.float32)
+    assert (mine != exact).mean() < 1e-3          # the oracle's pow is correctly rounded almost everywhere
+
+
+def _warp_literal_torch(image, depth, md, sign):
+    """forward_warp_stereo's algorithm, stated literally: ascending-depth argsort, floor scatters, then
+    ceil scatters of the frac > 0.3 subset, last writer wins."""
+    c, h, w = image.shape
+    d = torch.from_numpy(depth).flatten()
+    order = torch.argsort(d)
+    ys = (torch.arange(h * w) // w)[order]
+    xs = (torch.arange(h * w) % w).float()[order]
+    tx = xs + sign * (d * md)[order]
+    fl = tx.floor().long()
+    frac = tx - fl.float()
+    img = torch.from_numpy(image).reshape(c, -1)
+    out = torch.zeros(c, h * w)
+    wgt = torch.zeros(h * w)
+    ok = (fl >= 0) & (fl < w)
+    idx = (ys * w + fl)[ok]
+    for ch in range(c):
+        out[ch].scatter_(0, idx, img[ch, order[ok]])
+    wgt.scatter_(0, idx, (1.0 - frac)[ok])
+    ce = fl + 1
+    ok = (ce >= 0) & (ce < w) & (frac > 0.3)
+    idx = (ys * w + ce)[ok]
+    for ch in range(c):
+        out[ch].scatter_(0, idx, img[ch, order[ok]])
+    wgt.scatter_(0, idx, frac[ok])
+    return out.reshape(c, h, w).numpy(), (wgt > 0.1).reshape(h, w).numpy().astype(np.uint8)
+
+
+@pytest.mark.parametrize('kind', ['random', 'ties', 'ramp'])
+def test_sort_free_warp_equals_literal_argsort_scatter(kind):
+    rng = np.random.default_rng(5)
+    h, w, md = 40, 300, 37.5
+    img = rng.integers(0, 256, (3, h, w)).astype(np.float32)
+    if kind == 'random':
+        dep = rng.random((h, w), dtype=np.float32)
+    elif kind == 'ties':
+        dep = (np.rint(rng.random((h, w)) * 255) / 255).astype(np.float32)
+    else:
+        dep = np.tile(np.linspace(0, 1, w, dtype=np.float32)[None] ** 3, (h, 1))
+    for sign in (+1, -1):
+        ref_img, ref_mask = _warp_literal_torch(img, dep, md, sign)
+        mine_img, mine_mask = O.warp(img, dep, md, sign)
+        assert np.array_equal(mine_mask, ref_mask) and np.array_equal(mine_img, ref_img)
+
+
+@pytest.mark.parametrize('s', [1.0, 2.0, 5.0])
+def test_bilateral_vs_cv2(s):
+    img = make_rgb(150, 210, seed=1)
+    img[40:60, 50:90] = 0
+    d, sc, ss = O.bilateral_params(s)
+    mine = O.bilateral(img, d, sc, ss)
+    ref = cv2.bilateralFilter(img, d=d, sigmaColor=30, sigmaSpace=s * 25)
+    diff = np.abs(mine.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-4
+
+
+def _telea_masks(h, w):
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:h, 0:w]
+    m = [rng.random((h, w)) < 0.01]
+    v = np.zeros((h, w), bool); v[:, 50] = True; m.append(v)
+    v = np.zeros((h, w), bool); v[:, :25] = True; v[0:10, :] = True; m.append(v)
+    v = np.zeros((h, w), bool); v[0, 0] = v[h - 1, w - 1] = v[0, w - 1] = v[h - 1, 0] = True; v[0, 50:60] = True; m.append(v)
+    m.append((yy - 60) ** 2 + (xx - 80) ** 2 <= 35 ** 2)
+    m.append(cv2.dilate((rng.random((h, w)) < 0.15).astype(np.uint8), np.ones((3, 3), np.uint8)) > 0)
+    return m
+
+
+def test_telea_bit_exact_vs_cv2():
+    h, w = 120, 170
+    img = make_rgb(h, w, seed=3)
+    for hole in _telea_masks(h, w):
+        mask = hole.astype(np.uint8) * 255
+        ref = cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)
+        assert np.array_equal(O.telea(img, mask, 3), ref)
+        assert np.array_equal(O.dilate3(mask), cv2.dilate(mask, np.ones((3, 3), np.uint8)))
+
+
+def test_telea_known_answers():
+    """const-101 image with a 1-px hole inpaints to 102 (+0.5 and round both apply), const-100 to 100."""
+    for val, want in ((101, 102), (100, 100)):
+        img = np.full((20, 20, 3), val, np.uint8)
+        mask = np.zeros((20, 20), np.uint8)
+        mask[10, 10] = 255
+        out = O.telea(img, mask, 3)
+        assert out[10, 10, 0] == want == cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)[10, 10, 0]
+
+
+def test_truncation_not_rounding():
+    assert O.to_u8_trunc(np.array([254.999, 0.6, 300.0, -3.0], np.float32)).tolist() == [254, 0, 255, 0]

@@ -241,6 +241,7 @@ struct Slot {
     DevBuf st[2], tt[2], pstate[2], tile_u8[2], tile_i32[2], qkey[2], qidx[2];
     DevBuf tabs;        // lanczos + axis tables
     DevBuf scalars;     // FrameScalars
+    DevBuf tstats;      // Telea phase counters (VSC_TELEA_STATS builds)
     FrameScalars* h_scalars = nullptr;   // pinned mirror
     // table cache key
     int kH = 0, kW = 0, kSW = 0, kHs = 0, kWs = 0;
@@ -534,6 +535,11 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
     a.Hs = Hs; a.Ws = Ws; a.tw = (Ws + TG - 1) / TG; a.th = (Hs + TG - 1) / TG;
     a.keep_x0[0] = k0a; a.keep_x1[0] = k1a; a.keep_x0[1] = k0b; a.keep_x1[1] = k1b;
     a.nviews = nviews;
+#ifdef VSC_TELEA_STATS
+    if (s.tstats.ensure(64 * 8)) return VSC_E_NOMEM;
+    CU(cudaMemsetAsync(s.tstats.p, 0, 64 * 8, s.stream));
+    a.stats = s.tstats.as<unsigned long long>();
+#endif
     const size_t nt = (size_t)a.tw * a.th;
     uchar4* imgs[2] = {img0, img1};
     const uint8_t* valids[2] = {valid0, valid1};
@@ -569,7 +575,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
     telea_cluster_alloc_kernel<<<tgrid, kThreads, 0, s.stream>>>(a); KCHECK(s);
     prof_begin(s, "telea_cluster_fill_kernel");
     telea_cluster_fill_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);  KCHECK(s);
-    dim3 cgrid(ctx->sm_count * 2, nviews);   // persistent CTAs pulling clusters from a queue
+    dim3 cgrid(ctx->sm_count * 4, nviews);   // persistent CTAs pulling clusters from a queue
     prof_begin(s, "telea_cluster_kernel");
     telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
     KCHECK(s);
@@ -1062,5 +1068,16 @@ extern "C" int vsc_timer_end(vsc_ctx* ctx, float* ms) {
     CU(cudaEventRecord(ctx->t1, ctx->tstream));
     CU(cudaEventSynchronize(ctx->t1));
     CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return VSC_OK;
+}
+
+// debug: Telea phase counters of slot 0 (all zero unless built with -DVSC_TELEA_STATS)
+extern "C" int vsc_debug_telea_stats(vsc_ctx* ctx, unsigned long long* out64) {
+    if (!ctx || !out64) return fail(VSC_E_INVALID, "null argument");
+    Slot& s = ctx->slots[0];
+    memset(out64, 0, 64 * 8);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    if (s.tstats.p) CU(cudaMemcpy(out64, s.tstats.p, 64 * 8, cudaMemcpyDeviceToHost));
     return VSC_OK;
 }

@@ -59,6 +59,7 @@ struct TeleaArgs {
     int Hs, Ws, tw, th;
     int keep_x0[2], keep_x1[2];
     int nviews;
+    unsigned long long* stats;   // optional [2 views][2 passes][16] counters (VSC_TELEA_STATS builds)
 };
 
 // ---- 1. morphology ----------------------------------------------------------------------------
@@ -221,27 +222,69 @@ __global__ void telea_cluster_fill_kernel(const __grid_constant__ TeleaArgs a) {
 struct TapConst { signed char dk[32]; signed char dl[32]; float dst[32]; };
 __constant__ TapConst c_taps;   // 28 taps of the radius-3 disc in k-major raster order (centre excluded)
 
+// Per-warp shared-memory window around the pixel being popped.  Every access of one pop (fast-marching
+// solve + Telea weights + gradients) stays within 5 pixels of the popped position, so the window is
+// loaded once per pop with independent, coalesced-by-row loads (one memory round trip) and all the
+// dependent arithmetic then runs out of shared memory; results are written through to global memory.
+constexpr int WIN_R = 5, WIN_D = 2 * WIN_R + 1, WIN_S = WIN_D + 1;
+struct TapTable { int dk[32]; int dl[32]; float dst[32]; };
+struct WarpWin {
+    unsigned char st[WIN_D * WIN_S];
+    float tt[WIN_D * WIN_D];
+    unsigned img[WIN_D * WIN_D];
+    float taps[28 * 10];
+};
+
 struct Marcher {
     const TeleaView& V;
     int Hs, Ws;
     int lane;
+    WarpWin* w;
+    const TapTable* tp;   // shared-memory copy of the tap constants (constant memory would serialise per lane)
+    int wy0, wx0;   // image coordinates of window element (0,0)
     __device__ __forceinline__ bool inb(int y, int x) const { return y >= 0 && y < Hs && x >= 0 && x < Ws; }
-    // flags / T with the 1-pixel KNOWN frame (t = 1e6) that cv2.inpaint adds around the image
+    // (re)load the window of radius r <= WIN_R centred on (yc, xc); pixels outside the image read as the
+    // 1-pixel KNOWN frame (t = 1e6) that cv2.inpaint adds around the image
+    template <int R, bool WITH_IMG> __device__ __forceinline__ void load(int yc, int xc) {
+        wy0 = yc - WIN_R; wx0 = xc - WIN_R;
+        constexpr int D = 2 * R + 1, NIT = (D * D + 31) / 32;
+        unsigned char sv[NIT]; float tv[NIT]; unsigned iv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {       // issue every load before the first use
+            const int idx = lane + 32 * it;
+            const int ly = idx / D + (WIN_R - R), lx = idx % D + (WIN_R - R);
+            const int y = wy0 + ly, x = wx0 + lx;
+            sv[it] = 0; tv[it] = 1.0e6f; iv[it] = 0;
+            if (idx < D * D && inb(y, x)) {
+                const size_t p = (size_t)y * Ws + x;
+                sv[it] = V.st[p]; tv[it] = V.tt[p];
+                if (WITH_IMG) iv[it] = *reinterpret_cast<const unsigned*>(&V.img[p]);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int idx = lane + 32 * it;
+            if (idx < D * D) {
+                const int ly = idx / D + (WIN_R - R), lx = idx % D + (WIN_R - R);
+                w->st[ly * WIN_S + lx] = sv[it]; w->tt[ly * WIN_D + lx] = tv[it];
+                if (WITH_IMG) w->img[ly * WIN_D + lx] = iv[it];
+            }
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ unsigned char S(int y, int x) const { return w->st[(y - wy0) * WIN_S + (x - wx0)]; }
+    __device__ __forceinline__ float Traw(int y, int x) const { return w->tt[(y - wy0) * WIN_D + (x - wx0)]; }
     template <bool OUTER> __device__ __forceinline__ bool inside(int y, int x) const {
-        if (!inb(y, x)) return false;
-        const unsigned char s = V.st[(size_t)y * Ws + x];
+        const unsigned char s = S(y, x);
         return OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE);
     }
-    __device__ __forceinline__ float T_raw(int y, int x) const { return inb(y, x) ? V.tt[(size_t)y * Ws + x] : 1.0e6f; }
     // T as the inpainting pass sees it: the outer pass' distances are negated (icvCalcFMM negate=true)
     __device__ __forceinline__ float T_main(int y, int x) const {
-        if (!inb(y, x)) return 1.0e6f;
-        const size_t p = (size_t)y * Ws + x;
-        const float t = V.tt[p];
-        return ((V.st[p] & O_MASK) == O_CHANGE) ? -t : t;
+        const float t = Traw(y, x);
+        return ((S(y, x) & O_MASK) == O_CHANGE) ? -t : t;
     }
     template <bool OUTER> __device__ __forceinline__ float solve(int y1, int x1, int y2, int x2) const {
-        const double a11 = OUTER ? T_raw(y1, x1) : T_main(y1, x1), a22 = OUTER ? T_raw(y2, x2) : T_main(y2, x2);
+        const double a11 = OUTER ? Traw(y1, x1) : T_main(y1, x1), a22 = OUTER ? Traw(y2, x2) : T_main(y2, x2);
         const double m12 = a11 < a22 ? a11 : a22;
         double sol;
         if (!inside<OUTER>(y1, x1)) {
@@ -254,17 +297,24 @@ struct Marcher {
         else sol = __dadd_rn(1.0, m12);
         return (float)sol;
     }
+    // the four corner solves run on lanes 0..3; every lane returns the minimum
     template <bool OUTER> __device__ __forceinline__ float min4(int y, int x) const {
-        const float s0 = solve<OUTER>(y - 1, x, y, x - 1), s1 = solve<OUTER>(y + 1, x, y, x - 1);
-        const float s2 = solve<OUTER>(y - 1, x, y, x + 1), s3 = solve<OUTER>(y + 1, x, y, x + 1);
-        return fminf(fminf(s0, s1), fminf(s2, s3));
+        const int l = lane & 3;
+        const float s = solve<OUTER>(y + ((l & 1) ? 1 : -1), x, y, x + ((l & 2) ? 1 : -1));
+        const float a = fminf(s, __shfl_xor_sync(0xffffffffu, s, 1));
+        return fminf(a, __shfl_xor_sync(0xffffffffu, a, 2));
     }
-    __device__ __forceinline__ int pix(int y, int x, int c) const {
-        const uchar4 p = V.img[(size_t)y * Ws + x];
-        return c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    __device__ __forceinline__ int pix(int y, int x, int c) const { return (w->img[(y - wy0) * WIN_D + (x - wx0)] >> (8 * c)) & 0xff; }
+    // write-through updates by lane 0
+    __device__ __forceinline__ void set_T(int y, int x, float t) const {
+        V.tt[(size_t)y * Ws + x] = t; w->tt[(y - wy0) * WIN_D + (x - wx0)] = t;
+    }
+    __device__ __forceinline__ void set_S(int y, int x, unsigned char s) const {
+        V.st[(size_t)y * Ws + x] = s; w->st[(y - wy0) * WIN_S + (x - wx0)] = s;
     }
     // icvTeleaInpaintFMM body for one pixel (y,x) whose T was just set to `dist`; warp-cooperative
-    __device__ void inpaint(int y, int x, float dist, float* sm /* [28][10] */) const {
+    __device__ void inpaint(int y, int x, float dist) const {
+        float* sm = w->taps;
         // gradT (warp-uniform)
         float gtx, gty;
         {
@@ -278,16 +328,16 @@ struct Marcher {
         bool valid = false;
         float term[10];
         if (lane < 28) {
-            const int dk = c_taps.dk[lane], dl = c_taps.dl[lane];
+            const int dk = tp->dk[lane], dl = tp->dl[lane];
             const int ky = y + dk, kx = x + dl;
             if (inb(ky, kx) && !inside<false>(ky, kx)) {
                 valid = true;
                 const float ry = (float)(-dk), rx = (float)(-dl);
-                const float dst = c_taps.dst[lane];
+                const float dst = tp->dst[lane];
                 const float lev = (float)__ddiv_rn(1.0, __dadd_rn(1.0, fabs((double)__fsub_rn(T_main(ky, kx), dist))));
                 float dir = __fadd_rn(__fmul_rn(rx, gtx), __fmul_rn(ry, gty));
                 if (fabs((double)dir) <= 0.01) dir = 0.000001f;
-                const float w = fabsf(__fmul_rn(__fmul_rn(dst, lev), dir));
+                const float wgt = fabsf(__fmul_rn(__fmul_rn(dst, lev), dir));
                 const bool fr = !inside<false>(ky, kx + 1), fl = !inside<false>(ky, kx - 1);
                 const bool fd = !inside<false>(ky + 1, kx), fu = !inside<false>(ky - 1, kx);
                 const int km = ky + (ky == 0), kp = ky - (ky == Hs - 1);
@@ -301,11 +351,11 @@ struct Marcher {
                     if (fd) giy = fu ? __fmul_rn((float)(pix(kp + 1, lm, c) - pix(km - 1, lm, c)), 2.0f)
                                      : (float)(pix(kp + 1, lm, c) - pix(km, lm, c));
                     else giy = fu ? (float)(pix(kp, lm, c) - pix(km - 1, lm, c)) : 0.f;
-                    term[c] = __fmul_rn(w, (float)pix(ky, kx, c));
-                    term[3 + c] = __fmul_rn(w, __fmul_rn(gix, rx));
-                    term[6 + c] = __fmul_rn(w, __fmul_rn(giy, ry));
+                    term[c] = __fmul_rn(wgt, (float)pix(ky, kx, c));
+                    term[3 + c] = __fmul_rn(wgt, __fmul_rn(gix, rx));
+                    term[6 + c] = __fmul_rn(wgt, __fmul_rn(giy, ry));
                 }
-                term[9] = w;
+                term[9] = wgt;
             }
         }
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
@@ -315,13 +365,18 @@ struct Marcher {
         }
         __syncwarp();
         // lanes 0..9 each accumulate one quantity in tap (raster) order: Ia[3], Jx[3], Jy[3], s
+        // (adding +0 for an absent tap leaves the accumulator bit-identical: it is never -0)
         float acc = lane == 9 ? 1.0e-20f : 0.f;
-        if (lane < 10) {
+        {
+            const int col = lane < 10 ? lane : 0;
             const bool sub = lane >= 3 && lane < 9;
-            for (unsigned m = vm; m; m &= m - 1) {
-                const int L = __ffs(m) - 1;
-                const float t = sm[L * 10 + lane];
-                acc = sub ? __fsub_rn(acc, t) : __fadd_rn(acc, t);
+            float t[28];
+#pragma unroll
+            for (int L = 0; L < 28; L++) t[L] = sm[L * 10 + col];
+#pragma unroll
+            for (int L = 0; L < 28; L++) {
+                const float tv = ((vm >> L) & 1u) ? t[L] : 0.f;
+                acc = sub ? __fsub_rn(acc, tv) : __fadd_rn(acc, tv);
             }
         }
         const float s = __shfl_sync(0xffffffffu, acc, 9);
@@ -337,13 +392,14 @@ struct Marcher {
             const float sat = (float)val;
             outc = min(max(__float2int_rn(sat), 0), 255);
         }
-        const int c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
-                  c2 = __shfl_sync(0xffffffffu, outc, 2);
+        const unsigned c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
+                       c2 = __shfl_sync(0xffffffffu, outc, 2);
         __syncwarp();
         if (lane == 0) {
-            uchar4 p = V.img[(size_t)y * Ws + x];
-            p.x = (unsigned char)c0; p.y = (unsigned char)c1; p.z = (unsigned char)c2;
-            V.img[(size_t)y * Ws + x] = p;
+            const int li = (y - wy0) * WIN_D + (x - wx0);
+            const unsigned nv = (w->img[li] & 0xff000000u) | c0 | (c1 << 8) | (c2 << 16);
+            w->img[li] = nv;
+            V.img[(size_t)y * Ws + x] = make_uchar4((unsigned char)c0, (unsigned char)c1, (unsigned char)c2, (unsigned char)(nv >> 24));
         }
     }
 };
@@ -389,32 +445,57 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int TELEA_WARPS = 16;
-constexpr int TELEA_DC = 6;   // two pops closer than this (Chebyshev) are ordered; farther apart they commute
+constexpr int TELEA_WARPS = 8;
+// two pops of one generation closer than this (Chebyshev) are executed in queue order; farther apart they
+// commute.  Inpainting pop: reads within 5 of its position, writes within 1 -> 6.  Outer-ring pop: reads
+// within 2, writes within 1 -> 3.
+constexpr int TELEA_DC_MAIN = 6, TELEA_DC_OUTER = 3;
 
 struct MarchShared {
     int npool, npool2, ncur, next_e, gbase;
     unsigned tmin;
     int ci;
-    float taps[TELEA_WARPS][28 * 10];
+    WarpWin win[TELEA_WARPS];
+#ifdef VSC_TELEA_STATS
+    unsigned long long c_wait, c_pop, c_sort, c_part, c_total, n_pops, n_pix, n_gen, n_polls, c_load, c_inp, c_rel, c_min4;
+#endif
 };
 
 // One fast-marching pass over one cluster, executed by a whole CTA.
 //  * the queue is processed in generations (see file header); each generation is sorted CTA-wide
 //  * inside a generation the pops are executed as a dataflow: warps claim pops in sorted order and a pop
-//    starts once every earlier pop within TELEA_DC pixels has finished (pstate: (global pop index << 1) |
+//    starts once every earlier pop within TELEA_DC_* pixels has finished (pstate: (global pop index << 1) |
 //    done).  A pop touches pixels within 5 of its own position and writes within 1, so pops farther apart
 //    than 6 commute and the result is identical to the sequential order.
 //  * the FIFO tie-break of the reference's queue is (global pop index, neighbour q), which is exactly the
 //    order in which a sequential run would have pushed.
 template <bool OUTER>
-__device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw) {
+__device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw,
+                      unsigned long long* stats) {
     unsigned long long* pk[2] = {V.qkey[0] + qoff, V.qkey[1] + qoff};
     unsigned* pi[2] = {V.qidx[0] + qoff, V.qidx[1] + qoff};
     unsigned long long* cur_k = V.qkey[2] + qoff;
     unsigned* cur_i = V.qidx[2] + qoff;
     const int Ws = mc.Ws, Hs = mc.Hs, lane = mc.lane, wid = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.next_e = 0; sh.gbase = 1; sh.tmin = 0xffffffffu; }
+#ifdef VSC_TELEA_STATS
+    if (tid == 0) { sh.c_wait = sh.c_pop = sh.c_sort = sh.c_part = sh.n_pops = sh.n_pix = sh.n_gen = sh.n_polls = sh.c_load = sh.c_inp = sh.c_rel = sh.c_min4 = 0; }
+    const long long t_start = clock64();
+    long long t_mark;
+#define STAT_MARK() t_mark = clock64()
+#define STAT_ADD(field) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_mark)); } while (0)
+#define STAT_ADD0(field) do { if (tid == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_mark)); } while (0)
+#define STAT_INC(field, n) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(n)); } while (0)
+#define STAT_T0() const long long t_sub = clock64()
+#define STAT_T1(field) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_sub)); } while (0)
+#else
+#define STAT_T0()
+#define STAT_T1(field)
+#define STAT_MARK()
+#define STAT_ADD(field)
+#define STAT_ADD0(field)
+#define STAT_INC(field, n)
+#endif
     __syncthreads();
     // initial queue: the band pixels, T = 0, ordered by raster position (= linear index in the key)
     for (int ti = wid; ti < ntiles; ti += TELEA_WARPS) {
@@ -444,6 +525,7 @@ __device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, in
         if (npool == 0) break;
         unsigned long long* pool_k = pk[src]; unsigned* pool_i = pi[src];
         unsigned long long* next_k = pk[src ^ 1]; unsigned* next_i = pi[src ^ 1];
+        STAT_MARK();
         // generation = entries with T < Tmin + 0.7
         unsigned tmin = 0xffffffffu;
         for (int i = tid; i < npool; i += nt) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
@@ -464,8 +546,12 @@ __device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, in
         }
         __syncthreads();
         const int ncur = sh.ncur, gbase = sh.gbase;
+        STAT_ADD0(c_part);
+        STAT_MARK();
         block_sort(cur_k, cur_i, ncur);
         __syncthreads();
+        STAT_ADD0(c_sort);
+        if (tid == 0) { STAT_INC(n_gen, 1); STAT_INC(n_pops, ncur); }
         for (int e = tid; e < ncur; e += nt) V.pstate[cur_i[e]] = (unsigned)(gbase + e) << 1;
         __syncthreads();
         // dataflow over the sorted generation
@@ -477,8 +563,10 @@ __device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, in
             const unsigned p = cur_i[e];
             const unsigned G = (unsigned)(gbase + e);
             const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
+            STAT_MARK();
             // wait for every earlier pop within TELEA_DC
             {
+                constexpr int TELEA_DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
                 constexpr int D = 2 * TELEA_DC + 1;
                 bool pend[(D * D + 31) / 32];
 #pragma unroll
@@ -498,32 +586,40 @@ __device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, in
                         pend[r] = (v >> 1) < G && !(v & 1u);
                         any |= pend[r];
                     }
+                    STAT_INC(n_polls, 1);
                     if (!__any_sync(0xffffffffu, any)) break;
+                    __nanosleep(200);   // back off: spinning warps must not steal issue slots from the working ones
                 }
                 __syncwarp();
             }
-            if (OUTER && lane == 0) V.st[p] = (V.st[p] & ~O_MASK) | O_CHANGE;
+            STAT_ADD(c_wait);
+            STAT_MARK();
+            { STAT_T0(); mc.template load<OUTER ? 2 : WIN_R, !OUTER>(yy, xx); STAT_T1(c_load); }
+            if (OUTER && lane == 0) mc.set_S(yy, xx, (mc.S(yy, xx) & ~O_MASK) | O_CHANGE);
             __syncwarp();
 #pragma unroll 1
             for (int q = 0; q < 4; q++) {
                 const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
                 if (!mc.inb(y, x)) continue;
                 if (!mc.inside<OUTER>(y, x)) continue;
-                const size_t pn = (size_t)y * Ws + x;
-                const float dist = mc.min4<OUTER>(y, x);
-                if (lane == 0) V.tt[pn] = dist;
+                float dist;
+                { STAT_T0(); dist = mc.min4<OUTER>(y, x); STAT_T1(c_min4); }
                 __syncwarp();
-                if (!OUTER) mc.inpaint(y, x, dist, sh.taps[wid]);
+                if (lane == 0) mc.set_T(y, x, dist);
+                __syncwarp();
+                STAT_INC(n_pix, 1);
+                if (!OUTER) { STAT_T0(); mc.inpaint(y, x, dist); STAT_T1(c_inp); }
                 if (lane == 0) {
-                    const unsigned char s = V.st[pn];
-                    V.st[pn] = OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND);
+                    const unsigned char s = mc.S(y, x);
+                    mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
                     const int pos = atomicAdd(&sh.npool2, 1);
                     next_k[pos] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(G * 4u + (unsigned)q);
-                    next_i[pos] = (unsigned)pn;
+                    next_i[pos] = (unsigned)((size_t)y * Ws + x);
                 }
                 __syncwarp();
             }
-            if (lane == 0) st_release(&V.pstate[p], (G << 1) | 1u);
+            { STAT_T0(); if (lane == 0) st_release(&V.pstate[p], (G << 1) | 1u); __syncwarp(); STAT_T1(c_rel); }
+            STAT_ADD(c_pop);
         }
         __syncthreads();
         if (tid == 0) {
@@ -532,10 +628,25 @@ __device__ void march(const Marcher& mc, const TeleaView& V, MarchShared& sh, in
         src ^= 1;
         __syncthreads();
     }
+#ifdef VSC_TELEA_STATS
+    if (tid == 0 && stats) {
+        const unsigned long long tot = (unsigned long long)(clock64() - t_start);
+        atomicAdd(&stats[0], sh.c_wait); atomicAdd(&stats[1], sh.c_pop); atomicAdd(&stats[2], sh.c_sort);
+        atomicAdd(&stats[3], sh.c_part); atomicAdd(&stats[4], tot); atomicAdd(&stats[5], sh.n_pops);
+        atomicAdd(&stats[6], sh.n_pix); atomicAdd(&stats[7], sh.n_gen); atomicAdd(&stats[8], sh.n_polls);
+        atomicAdd(&stats[9], 1ull);
+        if (tot > stats[10]) {   // record of the slowest cluster (racy but good enough for a profile)
+            stats[10] = tot; stats[11] = sh.n_pops; stats[12] = sh.c_load; stats[13] = sh.c_min4; stats[14] = sh.c_inp; stats[15] = sh.c_rel;
+        }
+    }
+#endif
 }
 
 __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
     __shared__ MarchShared sh;
+    __shared__ TapTable tp;
+    if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int v = blockIdx.y;
     const TeleaView& V = a.v[v];
@@ -544,7 +655,7 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const _
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&a.fs->overflow, a.fs->qbump[v]);
         return;
     }
-    Marcher mc{V, a.Hs, a.Ws, lane};
+    Marcher mc{V, a.Hs, a.Ws, lane, &sh.win[threadIdx.x >> 5], &tp, 0, 0};
     const int cap = a.tw * a.th;
     while (true) {
         if (threadIdx.x == 0) sh.ci = atomicAdd(&a.fs->next[v], 1);
@@ -554,9 +665,9 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const _
         const int ci = i < nbig ? i : cap - 1 - (i - nbig);     // big clusters are queued first
         const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
         const int* tiles = V.tile_list + V.cl_toff[ci];
-        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw);
+        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.stats ? a.stats + (v * 2 + 0) * 16 : nullptr);
         __syncthreads();
-        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw);
+        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.stats ? a.stats + (v * 2 + 1) * 16 : nullptr);
         __syncthreads();
     }
 }

@@ -1,0 +1,141 @@
+"""Frame-range sharding of one clip across the GPUs of a box, plus in-order publishing.
+
+Frames are independent (process_frame is a pure function of one (rgb, depth, params) triple,
+reference: helper/stereo_core.py:225-311; the driver treats frames idempotently,
+sbs_generator.py:178-185), so sharding needs no collective: every rank takes its own frames and
+only a barrier closes the clip.
+
+Constraint inherited from the orchestrator: progress and "done" are inferred from
+the MAX sbs_*.png number (helper/workflow_metrics.py:208-227) and the chunker needs gap-free
+ranges (chunk_generator.py:140-178).  Two measures keep that true with several writers:
+  * block-cyclic assignment (small blocks dealt round-robin) so that all ranks advance through
+    the clip together instead of one rank racing ahead in the last block;
+  * `InOrderPublisher`: workers write `sbs_N.png` under a hidden temporary name and the publisher
+    renames files into place strictly in frame order, so a visible sbs_N.png implies that every
+    pending frame before it is visible too.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import time
+from typing import Callable, List, Optional, Sequence, Tuple
+
+__all__ = ['contiguous_ranges', 'block_cyclic', 'shard_items', 'InOrderPublisher', 'dist_env', 'barrier', 'all_reduce_max']
+
+
+def contiguous_ranges(n: int, world: int) -> List[Tuple[int, int]]:
+    """GPU g of G gets items [g*ceil(n/G), (g+1)*ceil(n/G)) (SURVEY 8(e) 'Partitioning')."""
+    if world < 1:
+        raise ValueError('world must be >= 1')
+    per = -(-n // world) if n else 0
+    return [(min(g * per, n), min((g + 1) * per, n)) for g in range(world)]
+
+
+def block_cyclic(n: int, world: int, rank: int, block: int = 16) -> List[int]:
+    """Indices of rank `rank`: blocks of `block` consecutive items dealt round-robin."""
+    if not (0 <= rank < world):
+        raise ValueError('rank out of range')
+    out: List[int] = []
+    for b0 in range(rank * block, n, world * block):
+        out.extend(range(b0, min(b0 + block, n)))
+    return out
+
+
+def shard_items(items: Sequence, world: int, rank: int, block: int = 16, mode: str = 'block_cyclic') -> list:
+    if mode == 'contiguous':
+        a, b = contiguous_ranges(len(items), world)[rank]
+        return list(items[a:b])
+    return [items[i] for i in block_cyclic(len(items), world, rank, block)]
+
+
+class InOrderPublisher:
+    """Renames finished outputs into place strictly in the order of `final_paths`.
+
+    Workers (any rank / process) call `staged_path(final)` to know where to write and
+    `mark_ready(final)` when the file is complete (an atomic rename to `<final>.ready`); one publisher
+    (rank 0) runs `publish_available()` / `run()` which moves `.ready` files to their final names in
+    order and stops at the first one that is not ready yet.
+    """
+
+    def __init__(self, final_paths: Sequence[str]):
+        self.final_paths = [str(p) for p in final_paths]
+        self._next = 0
+        self._stop = threading.Event()
+
+    @staticmethod
+    def staged_path(final: str) -> str:
+        d, b = os.path.split(str(final))
+        return os.path.join(d, '.' + b + '.part')
+
+    @staticmethod
+    def ready_path(final: str) -> str:
+        return str(final) + '.ready'
+
+    @classmethod
+    def mark_ready(cls, final: str) -> None:
+        os.replace(cls.staged_path(final), cls.ready_path(final))
+
+    def publish_available(self) -> int:
+        n = 0
+        while self._next < len(self.final_paths):
+            final = self.final_paths[self._next]
+            ready = self.ready_path(final)
+            if os.path.exists(ready):
+                os.replace(ready, final)
+            elif not os.path.exists(final):
+                break
+            self._next += 1
+            n += 1
+        return n
+
+    @property
+    def published(self) -> int:
+        return self._next
+
+    def done(self) -> bool:
+        return self._next >= len(self.final_paths)
+
+    def run(self, poll_s: float = 0.05, on_progress: Optional[Callable[[int], None]] = None, timeout_s: Optional[float] = None) -> bool:
+        t0 = time.time()
+        while not self.done() and not self._stop.is_set():
+            if self.publish_available() and on_progress:
+                on_progress(self._next)
+            if self.done():
+                break
+            if timeout_s is not None and time.time() - t0 > timeout_s:
+                return False
+            time.sleep(poll_s)
+        return self.done()
+
+    def stop(self) -> None:
+        self._stop.set()
+
+
+# ---- torch.distributed plumbing (NCCL on GPUs, gloo in CPU tests); no data-path collective -------------
+def dist_env() -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment (1 process per GPU)."""
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+
+
+def barrier() -> None:
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+    except ImportError:
+        pass
+
+
+def all_reduce_max(value: float, device: str = 'cpu') -> float:
+    """max over ranks of a host scalar (used for timing: a multi-GPU number is the slowest rank's)."""
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            t = torch.tensor([value], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+    except ImportError:
+        pass
+    return float(value)
