@@ -30,6 +30,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')   # one hardware queue per frame slot (before CUDA init)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(ROOT, 'video-stereo-converter_b200')]
 
@@ -296,8 +297,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=24, help='frames per step per GPU')
-    ap.add_argument('--slots', type=int, default=8, help='frames in flight per GPU')
+    ap.add_argument('--batch', type=int, default=96, help='frames per step per GPU')
+    ap.add_argument('--slots', type=int, default=30, help='frames in flight per GPU')
     ap.add_argument('--cpu-frames', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

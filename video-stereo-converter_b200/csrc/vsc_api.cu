@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -311,6 +312,7 @@ extern "C" int vsc_create(int device, int n_slots, vsc_ctx** out) {
     if (!out) return fail(VSC_E_INVALID, "null out pointer");
     *out = nullptr;
     if (n_slots < 1 || n_slots > 64) return fail(VSC_E_INVALID, "n_slots must be in [1,64]");
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // one hardware queue per slot stream (no effect once a context exists)
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -558,7 +560,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
         V.pstate = s.pstate[b].as<unsigned>();
         V.qcap = (int)s.qcap;
     }
-    for (int v = 0; v < nviews; v++) CU(cudaMemsetAsync(s.pstate[v].p, 0x01, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'done'
+    for (int v = 0; v < nviews; v++) CU(cudaMemsetAsync(s.pstate[v].p, 0xff, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'task done'
     dim3 pgrid((Ws + 31) / 32, (Hs + 31) / 32, nviews), pblock(32, 8);
     prof_begin(s, "telea_prepare_kernel");
     telea_prepare_kernel<<<pgrid, pblock, 0, s.stream>>>(a);

@@ -445,30 +445,40 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int TELEA_WARPS = 8;
-// two pops of one generation closer than this (Chebyshev) are executed in queue order; farther apart they
-// commute.  Inpainting pop: reads within 5 of its position, writes within 1 -> 6.  Outer-ring pop: reads
-// within 2, writes within 1 -> 3.
-constexpr int TELEA_DC_MAIN = 6, TELEA_DC_OUTER = 3;
+constexpr int TELEA_WARPS = 16;
+// Two compute tasks of one generation whose pixels are closer than this (Chebyshev) run in queue order;
+// farther apart they commute.  Inpainting a pixel reads flags / T / colours within 4 of it and writes only
+// the pixel itself -> 4.  An outer-ring distance reads the 4-neighbours and writes the pixel -> 1.
+constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
 
 struct MarchShared {
-    int npool, npool2, ncur, next_e, gbase;
+    int npool, npool2, ncur, ntask, next_t, gbase, scan_total;
     unsigned tmin;
     int ci;
+    int wsum[TELEA_WARPS];
     WarpWin win[TELEA_WARPS];
 #ifdef VSC_TELEA_STATS
     unsigned long long c_wait, c_pop, c_sort, c_part, c_total, n_pops, n_pix, n_gen, n_polls, c_load, c_inp, c_rel, c_min4;
 #endif
 };
 
+// pstate word per pixel: (order key << 2) | kind | done   kind: bit1 (1 = compute task, 0 = queue pop)
+//   pop  of the current generation : (G << 2) | 1              G = global pop index (rank in sorted order)
+//   task pending                   : (K << 2) | 2              K = G*4 + q  (owner pop, neighbour index)
+//   task done / never touched      : (K << 2) | 3   /  0xffffffff
+__device__ __forceinline__ bool ps_is_pop(unsigned v) { return (v & 3u) == 1u; }
+__device__ __forceinline__ bool ps_pending_before(unsigned v, unsigned K) { return (v & 3u) == 2u && (v >> 2) < K; }
+
 // One fast-marching pass over one cluster, executed by a whole CTA.
-//  * the queue is processed in generations (see file header); each generation is sorted CTA-wide
-//  * inside a generation the pops are executed as a dataflow: warps claim pops in sorted order and a pop
-//    starts once every earlier pop within TELEA_DC_* pixels has finished (pstate: (global pop index << 1) |
-//    done).  A pop touches pixels within 5 of its own position and writes within 1, so pops farther apart
-//    than 6 commute and the result is identical to the sequential order.
-//  * the FIFO tie-break of the reference's queue is (global pop index, neighbour q), which is exactly the
-//    order in which a sequential run would have pushed.
+//  * the queue is processed in generations (see file header); each generation is sorted CTA-wide.
+//  * popping an entry computes those 4-neighbours that are still INSIDE; each such pixel is computed by the
+//    FIRST popped neighbour (its owner).  Ownership only depends on the sorted order, so the list of compute
+//    tasks of a generation, ordered by (owner rank, neighbour index) = the order in which a sequential run
+//    performs them, is built up front in parallel.
+//  * the tasks then run as a dataflow: warps claim tasks in order and a task starts once every earlier task
+//    within TELEA_DC_* pixels has finished (pstate).  Tasks farther apart commute, so the result is
+//    identical to the sequential order.
+//  * the FIFO tie-break of the reference's queue is the task key K, i.e. the sequential push order.
 template <bool OUTER>
 __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw,
                       unsigned long long* stats) {
@@ -477,7 +487,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
     unsigned long long* cur_k = V.qkey[2] + qoff;
     unsigned* cur_i = V.qidx[2] + qoff;
     const int Ws = mc.Ws, Hs = mc.Hs, lane = mc.lane, wid = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.next_e = 0; sh.gbase = 1; sh.tmin = 0xffffffffu; }
+    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.tmin = 0xffffffffu; if (OUTER) sh.gbase = 1; }
 #ifdef VSC_TELEA_STATS
     if (tid == 0) { sh.c_wait = sh.c_pop = sh.c_sort = sh.c_part = sh.n_pops = sh.n_pix = sh.n_gen = sh.n_polls = sh.c_load = sh.c_inp = sh.c_rel = sh.c_min4 = 0; }
     const long long t_start = clock64();
@@ -489,12 +499,12 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
 #define STAT_T0() const long long t_sub = clock64()
 #define STAT_T1(field) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_sub)); } while (0)
 #else
-#define STAT_T0()
-#define STAT_T1(field)
 #define STAT_MARK()
 #define STAT_ADD(field)
 #define STAT_ADD0(field)
 #define STAT_INC(field, n)
+#define STAT_T0()
+#define STAT_T1(field)
 #endif
     __syncthreads();
     // initial queue: the band pixels, T = 0, ordered by raster position (= linear index in the key)
@@ -526,7 +536,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
         unsigned long long* pool_k = pk[src]; unsigned* pool_i = pi[src];
         unsigned long long* next_k = pk[src ^ 1]; unsigned* next_i = pi[src ^ 1];
         STAT_MARK();
-        // generation = entries with T < Tmin + 0.7
+        // ---- generation = entries with T < Tmin + 0.7 ---------------------------------------------------
         unsigned tmin = 0xffffffffu;
         for (int i = tid; i < npool; i += nt) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
         tmin = __reduce_min_sync(0xffffffffu, tmin);
@@ -545,85 +555,137 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             }
         }
         __syncthreads();
-        const int ncur = sh.ncur, gbase = sh.gbase;
+        const int ncur = sh.ncur, gbase = sh.gbase, carry = sh.npool2;
         STAT_ADD0(c_part);
         STAT_MARK();
         block_sort(cur_k, cur_i, ncur);
         __syncthreads();
         STAT_ADD0(c_sort);
         if (tid == 0) { STAT_INC(n_gen, 1); STAT_INC(n_pops, ncur); }
-        for (int e = tid; e < ncur; e += nt) V.pstate[cur_i[e]] = (unsigned)(gbase + e) << 1;
-        __syncthreads();
-        // dataflow over the sorted generation
-        while (true) {
-            int e = 0;
-            if (lane == 0) e = atomicAdd(&sh.next_e, 1);
-            e = __shfl_sync(0xffffffffu, e, 0);
-            if (e >= ncur) break;
+        STAT_MARK();
+        // ---- mark the pops of this generation (and the outer pass' CHANGE flag, which nothing orders) -------
+        for (int e = tid; e < ncur; e += nt) {
             const unsigned p = cur_i[e];
-            const unsigned G = (unsigned)(gbase + e);
-            const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
-            STAT_MARK();
-            // wait for every earlier pop within TELEA_DC
-            {
-                constexpr int TELEA_DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
-                constexpr int D = 2 * TELEA_DC + 1;
-                bool pend[(D * D + 31) / 32];
+            V.pstate[p] = ((unsigned)(gbase + e) << 2) | 1u;
+            if (OUTER) V.st[p] = (V.st[p] & ~O_MASK) | O_CHANGE;
+        }
+        __syncthreads();
+        // ---- ownership: which INSIDE neighbours does pop e compute?  (mask of q in cur_k[e]) ---------------
+        for (int e0 = 0; e0 < ncur; e0 += nt) {
+            const int e = e0 + tid;
+            unsigned own = 0;
+            if (e < ncur) {
+                const unsigned p = cur_i[e];
+                const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
+                const unsigned G = (unsigned)(gbase + e);
 #pragma unroll
-                for (int r = 0; r < (D * D + 31) / 32; r++) {
+                for (int q = 0; q < 4; q++) {
+                    const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
+                    if (!mc.inb(y, x)) continue;
+                    const unsigned char s = V.st[(size_t)y * Ws + x];
+                    if (!(OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE))) continue;
+                    bool first = true;     // no 4-neighbour of (y,x) is popped earlier in this generation
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const int y2 = y + (r == 0 ? -1 : (r == 2 ? 1 : 0)), x2 = x + (r == 1 ? -1 : (r == 3 ? 1 : 0));
+                        if (!mc.inb(y2, x2)) continue;
+                        const unsigned v = V.pstate[(size_t)y2 * Ws + x2];
+                        if (ps_is_pop(v) && (v >> 2) >= (unsigned)gbase && (v >> 2) < G) first = false;
+                    }
+                    if (first) own |= 1u << q;
+                }
+                cur_k[e] = own;
+            }
+            // exclusive scan of popc(own) over the generation, chunk by chunk
+            const int c = __popc(own);
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane == 31) sh.wsum[wid] = inc;
+            __syncthreads();
+            int woff = 0;
+            for (int w2 = 0; w2 < wid; w2++) woff += sh.wsum[w2];
+            const int off = sh.ntask + woff + inc - c;
+            if (e < ncur && own) {
+                const unsigned p = cur_i[e];
+                const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
+                const unsigned G = (unsigned)(gbase + e);
+                int j = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (!(own & (1u << q))) continue;
+                    const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
+                    const unsigned pn = (unsigned)y * (unsigned)Ws + (unsigned)x;
+                    const unsigned K = G * 4u + (unsigned)q;
+                    next_i[carry + off + j] = pn;
+                    next_k[carry + off + j] = (unsigned long long)K;      // T is filled in when the task runs
+                    V.pstate[pn] = (K << 2) | 2u;
+                    j++;
+                }
+            }
+            __syncthreads();
+            if (tid == nt - 1) sh.ntask = off + c;     // last thread holds the inclusive total of this chunk
+            __syncthreads();
+        }
+        const int ntask = sh.ntask;
+        STAT_ADD0(c_part);
+        // ---- dataflow over the ordered tasks -------------------------------------------------------------
+        while (true) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(&sh.next_t, 1);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (j >= ntask) break;
+            const unsigned pn = next_i[carry + j];
+            const unsigned K = (unsigned)next_k[carry + j];
+            const int y = (int)(pn / (unsigned)Ws), x = (int)(pn - (unsigned)y * (unsigned)Ws);
+            STAT_MARK();
+            {   // wait for every earlier task within TELEA_DC
+                constexpr int DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
+                constexpr int D = 2 * DC + 1, NIT = (D * D + 31) / 32;
+                bool pend[NIT];
+#pragma unroll
+                for (int r = 0; r < NIT; r++) {
                     const int idx = lane + 32 * r;
-                    const int dy = idx / D - TELEA_DC, dx = idx % D - TELEA_DC;
-                    pend[r] = idx < D * D && mc.inb(yy + dy, xx + dx);
+                    pend[r] = idx < D * D && mc.inb(y + idx / D - DC, x + idx % D - DC);
                 }
                 while (true) {
                     bool any = false;
 #pragma unroll
-                    for (int r = 0; r < (D * D + 31) / 32; r++) {
+                    for (int r = 0; r < NIT; r++) {
                         if (!pend[r]) continue;
                         const int idx = lane + 32 * r;
-                        const int dy = idx / D - TELEA_DC, dx = idx % D - TELEA_DC;
-                        const unsigned v = ld_acquire(&V.pstate[(size_t)(yy + dy) * Ws + xx + dx]);
-                        pend[r] = (v >> 1) < G && !(v & 1u);
+                        const unsigned v = ld_acquire(&V.pstate[(size_t)(y + idx / D - DC) * Ws + x + idx % D - DC]);
+                        pend[r] = ps_pending_before(v, K);
                         any |= pend[r];
                     }
                     STAT_INC(n_polls, 1);
                     if (!__any_sync(0xffffffffu, any)) break;
-                    __nanosleep(200);   // back off: spinning warps must not steal issue slots from the working ones
+                    __nanosleep(100);   // back off: waiting warps must not steal issue slots from the working ones
                 }
                 __syncwarp();
             }
             STAT_ADD(c_wait);
             STAT_MARK();
-            { STAT_T0(); mc.template load<OUTER ? 2 : WIN_R, !OUTER>(yy, xx); STAT_T1(c_load); }
-            if (OUTER && lane == 0) mc.set_S(yy, xx, (mc.S(yy, xx) & ~O_MASK) | O_CHANGE);
+            { STAT_T0(); mc.template load<OUTER ? 1 : 4, !OUTER>(y, x); STAT_T1(c_load); }
+            float dist;
+            { STAT_T0(); dist = mc.min4<OUTER>(y, x); STAT_T1(c_min4); }
             __syncwarp();
-#pragma unroll 1
-            for (int q = 0; q < 4; q++) {
-                const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
-                if (!mc.inb(y, x)) continue;
-                if (!mc.inside<OUTER>(y, x)) continue;
-                float dist;
-                { STAT_T0(); dist = mc.min4<OUTER>(y, x); STAT_T1(c_min4); }
-                __syncwarp();
-                if (lane == 0) mc.set_T(y, x, dist);
-                __syncwarp();
-                STAT_INC(n_pix, 1);
-                if (!OUTER) { STAT_T0(); mc.inpaint(y, x, dist); STAT_T1(c_inp); }
-                if (lane == 0) {
-                    const unsigned char s = mc.S(y, x);
-                    mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
-                    const int pos = atomicAdd(&sh.npool2, 1);
-                    next_k[pos] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(G * 4u + (unsigned)q);
-                    next_i[pos] = (unsigned)((size_t)y * Ws + x);
-                }
-                __syncwarp();
+            if (lane == 0) mc.set_T(y, x, dist);
+            __syncwarp();
+            STAT_INC(n_pix, 1);
+            if (!OUTER) { STAT_T0(); mc.inpaint(y, x, dist); STAT_T1(c_inp); }
+            if (lane == 0) {
+                const unsigned char s = mc.S(y, x);
+                mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
+                next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)K;
             }
-            { STAT_T0(); if (lane == 0) st_release(&V.pstate[p], (G << 1) | 1u); __syncwarp(); STAT_T1(c_rel); }
+            __syncwarp();
+            { STAT_T0(); if (lane == 0) st_release(&V.pstate[pn], (K << 2) | 3u); __syncwarp(); STAT_T1(c_rel); }
             STAT_ADD(c_pop);
         }
         __syncthreads();
         if (tid == 0) {
-            sh.gbase = gbase + ncur; sh.npool = sh.npool2; sh.npool2 = 0; sh.ncur = 0; sh.next_e = 0; sh.tmin = 0xffffffffu;
+            sh.gbase = gbase + ncur; sh.npool = carry + ntask; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.tmin = 0xffffffffu;
         }
         src ^= 1;
         __syncthreads();

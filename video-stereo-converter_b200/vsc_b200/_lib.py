@@ -6,6 +6,10 @@ import os
 
 import numpy as np
 
+# Frames in flight live on separate CUDA streams; with the default of 8 hardware work queues, streams beyond
+# the 8th alias onto the same queue and serialise.  Must be set before the CUDA context is created.
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('VSC_B200_LIB', os.path.normpath(os.path.join(_HERE, '..', 'lib', 'libvsc_b200.so')))
 
