@@ -301,9 +301,9 @@ static int set_smem_attrs() {
     CU(cudaFuncSetAttribute(lanczos_depth_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(lanczos_depth_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(lanczos_depth_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(depth_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(depth_front_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(depth_front_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(bilateral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return VSC_OK;
 }
@@ -456,8 +456,12 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
         const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4;
         dim3 grid((g.ss_w + DF_T - 1) / DF_T, (g.ss_h + DF_T - 1) / DF_T);
         prof_begin(s, "depth_front_kernel");
-        depth_front_kernel<<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
-                                                               g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
+        if (g.blur_k == 31)
+            depth_front_kernel<31><<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
+                                                                       g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
+        else
+            depth_front_kernel<0><<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
+                                                                      g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
     } else {
         dim3 grid((g.ss_w + kThreads * 4 - 1) / (kThreads * 4), g.ss_h);
         prof_begin(s, "depth_point_kernel");
@@ -504,7 +508,15 @@ static int run_bilateral(vsc_ctx* ctx, Slot& s, int Hs, int Ws, double smoothing
     const size_t smem = (768 + (size_t)TW * TW) * 4;
     dim3 grid((Ws + 31) / 32, (Hs + 31) / 32, nviews), block(32, 8);
     prof_begin(s, "bilateral_kernel");
-    bilateral_kernel<<<grid, block, smem, s.stream>>>(a);
+    switch (a.taps.radius) {
+        case 2: bilateral_kernel<2><<<grid, block, smem, s.stream>>>(a); break;
+        case 3: bilateral_kernel<3><<<grid, block, smem, s.stream>>>(a); break;
+        case 4: bilateral_kernel<4><<<grid, block, smem, s.stream>>>(a); break;
+        case 5: bilateral_kernel<5><<<grid, block, smem, s.stream>>>(a); break;
+        case 6: bilateral_kernel<6><<<grid, block, smem, s.stream>>>(a); break;
+        case 7: bilateral_kernel<7><<<grid, block, smem, s.stream>>>(a); break;
+        default: return fail(VSC_E_INVALID, "bilateral radius %d not supported", a.taps.radius);
+    }
     KCHECK(s);
     return VSC_OK;
 }

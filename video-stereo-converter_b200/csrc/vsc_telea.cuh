@@ -63,67 +63,85 @@ struct TeleaArgs {
 };
 
 // ---- 1. morphology ----------------------------------------------------------------------------
+// One CTA = 32x32 pixels.  The hole mask of the tile (+5 apron) is packed into one 64-bit word per row, so
+// the 3x3 dilation, the 4-neighbour band, and the 7x7 / 9x9 neighbourhood tests are a few shifts and ORs
+// per row instead of an 81-tap loop per pixel.
+__device__ __forceinline__ unsigned long long hdil(unsigned long long m, int r) {   // horizontal dilation by r
+    unsigned long long o = m;
+    for (int d = 1; d <= r; d++) o |= (m << d) | (m >> d);
+    return o;
+}
 __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_constant__ TeleaArgs a) {
-    __shared__ unsigned char h0[42][44];   // hole0 (apron 5)
-    __shared__ unsigned char M[40][44];    // dilated mask (apron 4)
-    __shared__ int cnt[16], need[16];
+    __shared__ unsigned long long h0[42], M[42], B[42], R3[42], N4[42];
     const int v = blockIdx.z;
     const TeleaView& V = a.v[v];
     const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    if (tid < 16) { cnt[tid] = 0; need[tid] = 0; }
-    for (int i = tid; i < 42 * 42; i += kThreads) {
-        const int iy = i / 42, ix = i - iy * 42;
-        const int y = Y0 - 5 + iy, x = X0 - 5 + ix;
-        unsigned char h = 0;
-        if (y >= 0 && y < a.Hs && x >= 0 && x < a.Ws) h = V.valid[(size_t)y * a.Ws + x] ? 0 : 1;
-        h0[iy][ix] = h;
+    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wid = threadIdx.y;
+    // bit i of a row word <-> image column X0 - 5 + i; row r <-> image row Y0 - 5 + r
+    for (int r = wid; r < 42; r += 8) {
+        const int y = Y0 - 5 + r;
+        const bool yin = y >= 0 && y < a.Hs;
+        const int x0 = X0 - 5 + lane, x1 = X0 + 27 + lane;
+        const bool b0 = yin && x0 >= 0 && x0 < a.Ws && V.valid[(size_t)y * a.Ws + x0] == 0;
+        const bool b1 = yin && lane < 10 && x1 < a.Ws && V.valid[(size_t)y * a.Ws + x1] == 0;
+        const unsigned w0 = __ballot_sync(0xffffffffu, b0), w1 = __ballot_sync(0xffffffffu, b1);
+        if (lane == 0) h0[r] = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+    }
+    // columns / rows of the tile window that lie inside the image
+    unsigned long long cm = 0;
+    for (int i = 0; i < 42; i++) { const int x = X0 - 5 + i; if (x >= 0 && x < a.Ws) cm |= 1ull << i; }
+    __syncthreads();
+    if (tid < 42) {
+        const int r = tid, y = Y0 - 5 + r;
+        unsigned long long m = 0;
+        if (r >= 1 && r <= 40 && y >= 0 && y < a.Hs) m = (hdil(h0[r - 1], 1) | hdil(h0[r], 1) | hdil(h0[r + 1], 1)) & cm;
+        M[r] = m;
     }
     __syncthreads();
-    for (int i = tid; i < 40 * 40; i += kThreads) {
-        const int iy = i / 40, ix = i - iy * 40;   // M coords: image (Y0-4+iy, X0-4+ix) = h0 (iy+1, ix+1)
-        const int y = Y0 - 4 + iy, x = X0 - 4 + ix;
-        unsigned char m = 0;
-        if (y >= 0 && y < a.Hs && x >= 0 && x < a.Ws) {
-#pragma unroll
-            for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++) m |= h0[iy + dy][ix + dx];
+    if (tid < 42) {
+        const int r = tid, y = Y0 - 5 + r;
+        unsigned long long band = 0, n3 = 0, n4 = 0;
+        if (r >= 5 && r < 37 && y < a.Hs) {       // only the 32 tile rows are consumed below
+            const unsigned long long m = M[r];
+            band = ~m & (M[r - 1] | M[r + 1] | (m << 1) | (m >> 1)) & cm;
+            for (int d = -4; d <= 4; d++) {
+                n4 |= hdil(M[r + d], 4);
+                if (d >= -3 && d <= 3) n3 |= hdil(M[r + d], 3);
+            }
         }
-        M[iy][ix] = m;
+        B[r] = band; R3[r] = n3; N4[r] = n4;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int ly = threadIdx.y + 8 * j, lx = threadIdx.x;
+        const int ly = wid + 8 * j, lx = lane;
         const int y = Y0 + ly, x = X0 + lx;
         if (y >= a.Hs || x >= a.Ws) continue;
-        const int my = ly + 4, mx = lx + 4;
-        const unsigned char m = M[my][mx];
-        const unsigned char band = !m && (M[my - 1][mx] | M[my + 1][mx] | M[my][mx - 1] | M[my][mx + 1]);
-        unsigned char near3 = 0, near4 = 0;
-        for (int dy = -4; dy <= 4; dy++)
-            for (int dx = -4; dx <= 4; dx++) {
-                const unsigned char q = M[my + dy][mx + dx];
-                near4 |= q;
-                if (dy >= -3 && dy <= 3 && dx >= -3 && dx <= 3) near3 |= q;
-            }
-        const unsigned char ring = !m && !band && near3;
+        const int r = ly + 5, b = lx + 5;
+        const unsigned m = (unsigned)(M[r] >> b) & 1u, band = (unsigned)(B[r] >> b) & 1u;
+        const unsigned ring = ((unsigned)(R3[r] >> b) & 1u) & ~m & ~band;
         const size_t p = (size_t)y * a.Ws + x;
-        V.st[p] = (m ? F_INSIDE : 0) | (ring ? O_INSIDE : 0) | (band ? ST_BAND0 : 0);
-        if (near4) V.tt[p] = band ? 0.f : 1.0e6f;
-        if (m | band | ring) {
-            const int t = (ly >> 3) * 4 + (lx >> 3);
-            atomicAdd(&cnt[t], 1);
-            if (m && x >= a.keep_x0[v] && x < a.keep_x1[v]) need[t] = 1;
-        }
+        V.st[p] = (unsigned char)((m ? F_INSIDE : 0) | (ring ? O_INSIDE : 0) | (band ? ST_BAND0 : 0));
+        if ((N4[r] >> b) & 1ull) V.tt[p] = band ? 0.f : 1.0e6f;
     }
-    __syncthreads();
     if (tid < 16) {
-        const int ty = blockIdx.y * 4 + (tid >> 2), tx = blockIdx.x * 4 + (tid & 3);
+        const int t4y = tid >> 2, t4x = tid & 3;
+        const int ty = blockIdx.y * 4 + t4y, tx = blockIdx.x * 4 + t4x;
         if (ty < a.th && tx < a.tw) {
-            V.tile_cnt[ty * a.tw + tx] = (unsigned char)cnt[tid];
-            V.tile_need[ty * a.tw + tx] = (unsigned char)need[tid];
+            unsigned long long keep = 0;
+            for (int i = 0; i < 8; i++) { const int x = X0 + 8 * t4x + i; if (x >= a.keep_x0[v] && x < a.keep_x1[v]) keep |= 1ull << i; }
+            int cnt = 0, need = 0;
+            for (int i = 0; i < 8; i++) {
+                const int r = 5 + 8 * t4y + i, sh = 5 + 8 * t4x;
+                const unsigned long long m = (M[r] >> sh) & 0xffull, bd = (B[r] >> sh) & 0xffull, rg = (R3[r] >> sh) & 0xffull;
+                // rows / columns outside the image carry no M, band or ring bits: M is masked, band is masked with cm,
+                // and the ring excludes nothing there but R3 rows beyond the image are zero (r < 37 && y < Hs above)
+                const unsigned long long inimg = (cm >> sh) & 0xffull;
+                cnt += __popcll((m | bd | (rg & ~m & ~bd)) & inimg);
+                need |= (m & keep) != 0;
+            }
+            V.tile_cnt[ty * a.tw + tx] = (unsigned char)cnt;
+            V.tile_need[ty * a.tw + tx] = (unsigned char)need;
         }
     }
 }
