@@ -64,6 +64,8 @@ class ClockSampler:
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
     def _run(self):
+        if os.environ.get('VSC_BENCH_NO_CLOCKS'):
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
@@ -244,8 +246,15 @@ def run_ours(args, rank, world, local_rank):
     return out
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    os.environ['OMP_NUM_THREADS'] = str(n)
+
+
 def cpu_baseline(sample_frames=1, h=H, w=W, warm=False):
     """Oracle port of the reference CPU path on this box's host cores (bounded sample)."""
+    _use_all_host_threads()
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle as O
     O.build()
@@ -266,6 +275,7 @@ def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference's own implementation, rank 0 only."""
     if rank != 0:
         return None
+    _use_all_host_threads()
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle as O
     O.build()

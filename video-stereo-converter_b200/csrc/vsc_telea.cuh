@@ -38,11 +38,11 @@ struct TeleaView {
     float* tt;              // [Hs][Ws]
     // tile grid
     unsigned char* tile_cnt;   // [th*tw] number of M|band|ring pixels (<= 64)
-    unsigned char* tile_need;  // [th*tw] tile has an M pixel inside the kept window
+    unsigned char* tile_need;  // [th*tw] number of M pixels of the tile inside the kept window
     int* lab;                  // [th*tw] union-find parent, -1 = empty tile
     int* csize;                // [th*tw] per-root pixel count
     int* ctiles;               // [th*tw] per-root tile count
-    int* cneed;                // [th*tw] per-root needed flag
+    int* cneed;                // [th*tw] per-root number of M pixels inside the kept window
     int* cslot;                // [th*tw] per-root cluster slot
     // clusters
     int* cl_qoff;  int* cl_toff;  int* cl_ntiles;  int* cl_size;  int* cl_fill;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
         if (ty < a.th && tx < a.tw) {
             unsigned long long keep = 0;
             for (int i = 0; i < 8; i++) { const int x = X0 + 8 * t4x + i; if (x >= a.keep_x0[v] && x < a.keep_x1[v]) keep |= 1ull << i; }
-            int cnt = 0, need = 0;
+            int cnt = 0, need = 0;     // need = number of M pixels inside the kept window
             for (int i = 0; i < 8; i++) {
                 const int r = 5 + 8 * t4y + i, sh = 5 + 8 * t4x;
                 const unsigned long long m = (M[r] >> sh) & 0xffull, bd = (B[r] >> sh) & 0xffull, rg = (R3[r] >> sh) & 0xffull;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
                 // and the ring excludes nothing there but R3 rows beyond the image are zero (r < 37 && y < Hs above)
                 const unsigned long long inimg = (cm >> sh) & 0xffull;
                 cnt += __popcll((m | bd | (rg & ~m & ~bd)) & inimg);
-                need |= (m & keep) != 0;
+                need += __popcll(m & keep);
             }
             V.tile_cnt[ty * a.tw + tx] = (unsigned char)cnt;
             V.tile_need[ty * a.tw + tx] = (unsigned char)need;
@@ -199,7 +199,7 @@ __global__ void telea_ccl_flatten_kernel(const __grid_constant__ TeleaArgs a) {
             const int root = uf_find(V.lab, t);
             atomicAdd(&V.csize[root], (int)V.tile_cnt[t]);
             atomicAdd(&V.ctiles[root], 1);
-            if (V.tile_need[t]) atomicOr(&V.cneed[root], 1);
+            if (V.tile_need[t]) atomicAdd(&V.cneed[root], (int)V.tile_need[t]);
         }
     }
 }
@@ -215,7 +215,7 @@ __global__ void telea_cluster_alloc_kernel(const __grid_constant__ TeleaArgs a) 
             V.cl_qoff[ci] = atomicAdd(&a.fs->qbump[v], V.csize[t]);
             V.cl_toff[ci] = atomicAdd(&a.fs->tbump[v], V.ctiles[t]);
             V.cl_ntiles[ci] = V.ctiles[t];
-            V.cl_size[ci] = V.csize[t];
+            V.cl_size[ci] = V.cneed[t];      // hole pixels that the back end will read
             V.cl_fill[ci] = 0;
             V.cslot[t] = ci;
         }
@@ -470,7 +470,7 @@ constexpr int TELEA_WARPS = 16;
 constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
 
 struct MarchShared {
-    int npool, npool2, ncur, ntask, next_t, gbase, scan_total;
+    int npool, npool2, ncur, ntask, next_t, gbase, scan_total, need_left;
     unsigned tmin;
     int ci;
     int wsum[TELEA_WARPS];
@@ -499,7 +499,7 @@ __device__ __forceinline__ bool ps_pending_before(unsigned v, unsigned K) { retu
 //  * the FIFO tie-break of the reference's queue is the task key K, i.e. the sequential push order.
 template <bool OUTER>
 __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw,
-                      unsigned long long* stats) {
+                      int keep_x0, int keep_x1, unsigned long long* stats) {
     unsigned long long* pk[2] = {V.qkey[0] + qoff, V.qkey[1] + qoff};
     unsigned* pi[2] = {V.qidx[0] + qoff, V.qidx[1] + qoff};
     unsigned long long* cur_k = V.qkey[2] + qoff;
@@ -696,6 +696,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
                 const unsigned char s = mc.S(y, x);
                 mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
                 next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)K;
+                if (!OUTER && x >= keep_x0 && x < keep_x1) atomicSub(&sh.need_left, 1);
             }
             __syncwarp();
             { STAT_T0(); if (lane == 0) st_release(&V.pstate[pn], (K << 2) | 3u); __syncwarp(); STAT_T1(c_rel); }
@@ -707,6 +708,9 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
         }
         src ^= 1;
         __syncthreads();
+        // Everything still queued has a larger T than every pixel computed so far and can therefore not influence
+        // them; once all hole pixels inside the kept window are filled, the rest of the cluster is never read.
+        if (!OUTER && sh.need_left <= 0) break;
     }
 #ifdef VSC_TELEA_STATS
     if (tid == 0 && stats) {
@@ -745,9 +749,10 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const _
         const int ci = i < nbig ? i : cap - 1 - (i - nbig);     // big clusters are queued first
         const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
         const int* tiles = V.tile_list + V.cl_toff[ci];
-        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.stats ? a.stats + (v * 2 + 0) * 16 : nullptr);
+        if (threadIdx.x == 0) sh.need_left = V.cl_size[ci];
+        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.keep_x0[v], a.keep_x1[v], a.stats ? a.stats + (v * 2 + 0) * 16 : nullptr);
         __syncthreads();
-        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.stats ? a.stats + (v * 2 + 1) * 16 : nullptr);
+        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.keep_x0[v], a.keep_x1[v], a.stats ? a.stats + (v * 2 + 1) * 16 : nullptr);
         __syncthreads();
     }
 }
