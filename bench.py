@@ -120,37 +120,39 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     def device_step(step):
-        """one batch, inputs resident in HBM; returns nothing (caller times around it)"""
-        inflight = []
+        """one batch, inputs resident in HBM; a finished slot is reused at once (no head-of-line blocking)"""
+        free, busy = list(range(slots)), []
         for i in range(batch):
-            s = i % slots
-            if len(inflight) == slots:
-                gen.wait(inflight.pop(0))
+            if not free:
+                s = gen.wait_any(busy)
+                gen.wait(s)
+                busy.remove(s)
+                free.append(s)
+            s = free.pop(0)
             f = (step * batch + i) % n_distinct
             gen.submit_device(s, d_rgb[f].data_ptr(), d_dep[f].data_ptr(), DEPTH_DTYPE, H, W, d_out[s].data_ptr(), params)
-            inflight.append(s)
-        while inflight:
-            gen.wait(inflight.pop(0))
-
-    # pinned host copies of the inputs for the end-to-end leg (file I/O excluded, SURVEY 8(d))
-    pin_in = None
+            busy.append(s)
+        for s in busy:
+            gen.wait(s)
 
     def e2e_step(step):
-        inflight = []
+        free, busy, last = list(range(slots)), [], None
         for i in range(batch):
-            s = i % slots
-            if len(inflight) == slots:
-                gen.collect(inflight.pop(0), copy=False)
+            if not free:
+                s = gen.wait_any(busy)
+                last = gen.collect(s, copy=False)
+                busy.remove(s)
+                free.append(s)
+            s = free.pop(0)
             f = (step * batch + i) % n_distinct
             prgb, pdep = gen.pinned_inputs(s, H, W, DEPTH_DTYPE)
             # the loader's job: decode straight into the slot's pinned buffers (here: memcpy of a prepared frame)
             np.copyto(prgb, frames[f][0])
             np.copyto(pdep, frames[f][1])
             gen.submit_pinned(s, params)
-            inflight.append(s)
-        last = None
-        while inflight:
-            last = gen.collect(inflight.pop(0), copy=False)
+            busy.append(s)
+        for s in busy:
+            last = gen.collect(s, copy=False)
         return int(last[0, 0, 0])      # device->host read of the step's result
 
     def barrier():

@@ -95,6 +95,8 @@ int vsc_host_free(void *p);
 int vsc_submit(vsc_ctx *ctx, int slot, const uint8_t *rgb, const void *depth, int depth_dtype,
                int height, int width, const vsc_params *p, uint8_t *out_sbs);
 int vsc_wait(vsc_ctx *ctx, int slot);
+/* non-blocking: 1 if the slot's frame has finished (vsc_wait will not block), 0 if it is still running */
+int vsc_query(vsc_ctx *ctx, int slot);
 /* device-resident variant: inputs/outputs are device pointers on ctx's device; enqueues only
  * (no copies, no synchronisation); vsc_wait(slot) or vsc_sync to complete. */
 int vsc_submit_device(vsc_ctx *ctx, int slot, const uint8_t *d_rgb, const void *d_depth, int depth_dtype,

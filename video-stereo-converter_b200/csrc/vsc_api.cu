@@ -733,6 +733,16 @@ extern "C" int vsc_wait(vsc_ctx* ctx, int slot) {
     return VSC_OK;
 }
 
+extern "C" int vsc_query(vsc_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad context or slot");
+    Slot& s = ctx->slots[slot];
+    if (!s.busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slot);
+    cudaError_t e = cudaStreamQuery(s.stream);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return fail(VSC_E_CUDA, "stream query failed: %s", cudaGetErrorString(e));
+}
+
 extern "C" int vsc_sync(vsc_ctx* ctx) {
     if (!ctx) return fail(VSC_E_INVALID, "null context");
     int rc = VSC_OK;

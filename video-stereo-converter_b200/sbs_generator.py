@@ -117,7 +117,10 @@ def process_shard(pairs, output_dir: Path, params, device_index: int, slots: int
             if save_failed.is_set():
                 break
             if not free_slots:
-                s, it = inflight.pop(0)
+                # reuse whichever slot finishes first (a slow frame must not stall the others)
+                s = gen.wait_any([sl for sl, _ in inflight])
+                it = next(t for sl, t in inflight if sl == s)
+                inflight.remove((s, it))
                 save_futs.append(savers.submit(save, gen.collect(s), it))
                 free_slots.append(s)
             s = free_slots.pop(0)

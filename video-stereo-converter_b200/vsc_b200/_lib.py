@@ -20,7 +20,7 @@ GPU_ERROR_EXIT_CODE = 100      # sbs_generator.py:41
 EXPORTS = [
     'vsc_abi_version', 'vsc_last_error', 'vsc_default_params', 'vsc_create', 'vsc_destroy', 'vsc_device',
     'vsc_num_slots', 'vsc_geometry', 'vsc_process_frame', 'vsc_host_alloc', 'vsc_host_free', 'vsc_submit',
-    'vsc_wait', 'vsc_submit_device', 'vsc_sync', 'vsc_slot_stream', 'vsc_slot_elapsed_ms', 'vsc_slot_launches',
+    'vsc_wait', 'vsc_query', 'vsc_submit_device', 'vsc_sync', 'vsc_slot_stream', 'vsc_slot_elapsed_ms', 'vsc_slot_launches',
     'vsc_stage_lanczos', 'vsc_stage_depth', 'vsc_stage_warp', 'vsc_stage_bilateral', 'vsc_stage_inpaint',
     'vsc_stage_backend', 'vsc_stage_warp_f32', 'vsc_stage_normalize_f32', 'vsc_stage_gamma_f32',
     'vsc_set_profiling', 'vsc_slot_kernel_times', 'vsc_timer_begin', 'vsc_timer_end', 'vsc_debug_fetch',
@@ -78,6 +78,7 @@ def load():
     lib.vsc_submit.argtypes = [vp, i, vp, vp, i, i, i, C.POINTER(VscParams), vp]
     lib.vsc_submit_device.argtypes = [vp, i, vp, vp, i, i, i, C.POINTER(VscParams), vp]
     lib.vsc_wait.argtypes = [vp, i]
+    lib.vsc_query.argtypes = [vp, i]
     lib.vsc_sync.argtypes = [vp]
     lib.vsc_slot_stream.argtypes = [vp, i]
     lib.vsc_slot_stream.restype = vp

@@ -243,6 +243,26 @@ class StereoGenerator:
     def wait(self, slot: int) -> None:
         _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
 
+    def ready(self, slot: int) -> bool:
+        """True once the slot's frame has finished on the device (wait/collect will not block)."""
+        r = self._lib.vsc_query(self._ctx.handle, slot)
+        if r < 0:
+            _lib.check(r)
+        return r == 1
+
+    def wait_any(self, slots) -> int:
+        """Block until one of the given in-flight slots has finished; returns that slot (not yet collected)."""
+        import time
+        slots = list(slots)
+        spins = 0
+        while True:
+            for s in slots:
+                if self.ready(s):
+                    return s
+            spins += 1
+            if spins > 50:
+                time.sleep(0.0002)
+
     # -- measurement -------------------------------------------------------------------------------
     def timer_begin(self) -> None:
         _lib.check(self._lib.vsc_timer_begin(self._ctx.handle))
