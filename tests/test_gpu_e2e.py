@@ -100,6 +100,24 @@ def test_async_slots_match_sync(gen):
         assert np.array_equal(a, b)
 
 
+def test_ready_and_wait_any(gen):
+    frames = [make_pair(90, 160, seed=s) for s in range(5)]
+    ref = [gen.process_frame(r, d) for r, d in frames]
+    for s in range(3):
+        gen.submit(s, *frames[s])
+    done = []
+    pending = [0, 1, 2]
+    while pending:
+        s = gen.wait_any(pending)
+        assert gen.ready(s)
+        done.append((s, gen.collect(s)))
+        pending.remove(s)
+    for s, out in done:
+        assert np.array_equal(out, ref[s])
+    with pytest.raises(RuntimeError):
+        gen.ready(0)            # nothing in flight any more
+
+
 def test_module_level_helpers():
     import torch
     from vsc_b200 import apply_depth_gamma, forward_warp_stereo, normalize_depth

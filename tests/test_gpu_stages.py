@@ -222,6 +222,26 @@ def test_inpaint_crop_culling_keeps_window_exact(ctx):
     assert (out[:, :20] == 0).all()
 
 
+def test_inpaint_band_connected_to_window_stops_early(ctx):
+    """A border band linked to an in-window crack is one cluster.  The march may stop once every in-window
+    hole pixel is filled (later pops cannot influence earlier pixels): the window must be exact, and the deep
+    part of the band, which the back end never reads, is left untouched."""
+    h, w = 200, 300
+    img = make_rgb(h, w, seed=12)
+    hole = np.zeros((h, w), bool)
+    hole[:, 240:] = True                 # wide band touching the right border
+    hole[20:180, 232] = True             # crack 8 px left of the band: same cluster, inside the kept window
+    hole[60:64, 150:170] = True          # separate small blob inside the window
+    valid = (~hole).astype(np.uint8)
+    img[hole] = 0
+    k0, kw = 10, 228                     # kept columns [10, 238): crack yes, band no
+    out, ref = _inpaint_case(ctx, img, valid, keep=(k0, kw))
+    assert np.array_equal(out[:, k0:k0 + kw], ref[:, k0:k0 + kw])
+    assert (out[:, 280:] == 0).all() and (ref[:, 280:] != 0).any()     # the deep band was not marched
+    full, ref2 = _inpaint_case(ctx, img, valid)
+    assert np.array_equal(full, ref2)
+
+
 def test_inpaint_real_warp_masks(ctx):
     """Masks as the warp produces them at sharp depth edges (edge_softness=0)."""
     rgb, depth = make_pair(150, 260, seed=3)

@@ -589,10 +589,12 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
     telea_cluster_alloc_kernel<<<tgrid, kThreads, 0, s.stream>>>(a); KCHECK(s);
     prof_begin(s, "telea_cluster_fill_kernel");
     telea_cluster_fill_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);  KCHECK(s);
+#ifndef VSC_EXPERIMENT_NO_MARCH
     dim3 cgrid(ctx->sm_count * 4, nviews);   // persistent CTAs pulling clusters from a queue
     prof_begin(s, "telea_cluster_kernel");
     telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
     KCHECK(s);
+#endif
     return VSC_OK;
 }
 static int run_backend(Slot& s, const vsc_geom& g, double sharpen, const uchar4* v0, const uchar4* v1, uint8_t* d_out) {
