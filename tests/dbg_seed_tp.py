@@ -6,7 +6,7 @@ sys.path[:0] = [os.path.join(ROOT, 'video-stereo-converter_b200')]
 import numpy as np, torch
 from vsc_b200 import StereoGenerator, StereoParams
 from vsc_b200.synthetic import make_pair
-h, w, slots, n = 1080, 1920, 30, 30
+h, w, slots, n = 1080, 1920, int(os.environ.get('SLOTS', '30')), 60
 g = StereoGenerator('cuda:0', slots)
 d_out = [torch.empty((h, 2 * w, 3), dtype=torch.uint8, device='cuda') for _ in range(slots)]
 for seed in [int(a) for a in sys.argv[1:]]:

@@ -590,7 +590,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
     prof_begin(s, "telea_cluster_fill_kernel");
     telea_cluster_fill_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);  KCHECK(s);
 #ifndef VSC_EXPERIMENT_NO_MARCH
-    dim3 cgrid(ctx->sm_count * 4, nviews);   // persistent CTAs pulling clusters from a queue
+    dim3 cgrid(ctx->sm_count / 2, nviews);   // persistent CTAs pulling clusters from a queue (big clusters first)
     prof_begin(s, "telea_cluster_kernel");
     telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
     KCHECK(s);

@@ -470,7 +470,7 @@ constexpr int TELEA_WARPS = 16;
 constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
 
 struct MarchShared {
-    int npool, npool2, ncur, ntask, next_t, gbase, scan_total, need_left;
+    int npool, npool2, ncur, ntask, next_t, done_t, gbase, scan_total, need_left;
     unsigned tmin;
     int ci;
     int wsum[TELEA_WARPS];
@@ -505,7 +505,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
     unsigned long long* cur_k = V.qkey[2] + qoff;
     unsigned* cur_i = V.qidx[2] + qoff;
     const int Ws = mc.Ws, Hs = mc.Hs, lane = mc.lane, wid = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.tmin = 0xffffffffu; if (OUTER) sh.gbase = 1; }
+    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.done_t = 0; sh.tmin = 0xffffffffu; if (OUTER) sh.gbase = 1; }
 #ifdef VSC_TELEA_STATS
     if (tid == 0) { sh.c_wait = sh.c_pop = sh.c_sort = sh.c_part = sh.n_pops = sh.n_pix = sh.n_gen = sh.n_polls = sh.c_load = sh.c_inp = sh.c_rel = sh.c_min4 = 0; }
     const long long t_start = clock64();
@@ -660,25 +660,26 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             {   // wait for every earlier task within TELEA_DC
                 constexpr int DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
                 constexpr int D = 2 * DC + 1, NIT = (D * D + 31) / 32;
-                bool pend[NIT];
+                const unsigned* addr[NIT];
+                unsigned pmask = 0;
 #pragma unroll
                 for (int r = 0; r < NIT; r++) {
                     const int idx = lane + 32 * r;
-                    pend[r] = idx < D * D && mc.inb(y + idx / D - DC, x + idx % D - DC);
+                    const int yy = y + idx / D - DC, xx = x + idx % D - DC;
+                    addr[r] = &V.pstate[(size_t)min(max(yy, 0), Hs - 1) * Ws + min(max(xx, 0), Ws - 1)];
+                    if (idx < D * D && mc.inb(yy, xx) && ps_pending_before(ld_acquire(addr[r]), K)) pmask |= 1u << r;
                 }
-                while (true) {
-                    bool any = false;
+                STAT_INC(n_polls, 1);
+                while (__any_sync(0xffffffffu, pmask != 0)) {
+                    // Only the oldest unfinished tasks are on the critical path: poll them eagerly; the further a
+                    // claimed task is behind the completion front, the longer it sleeps (waiting warps must not
+                    // steal issue slots from the working ones).
+                    const int behind = j - *(volatile int*)&sh.done_t;
+                    __nanosleep(behind <= 2 ? 40 : min(behind * 150, 3000));
 #pragma unroll
-                    for (int r = 0; r < NIT; r++) {
-                        if (!pend[r]) continue;
-                        const int idx = lane + 32 * r;
-                        const unsigned v = ld_acquire(&V.pstate[(size_t)(y + idx / D - DC) * Ws + x + idx % D - DC]);
-                        pend[r] = ps_pending_before(v, K);
-                        any |= pend[r];
-                    }
+                    for (int r = 0; r < NIT; r++)
+                        if ((pmask >> r) & 1u) { if (!ps_pending_before(ld_acquire(addr[r]), K)) pmask &= ~(1u << r); }
                     STAT_INC(n_polls, 1);
-                    if (!__any_sync(0xffffffffu, any)) break;
-                    __nanosleep(100);   // back off: waiting warps must not steal issue slots from the working ones
                 }
                 __syncwarp();
             }
@@ -699,12 +700,12 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
                 if (!OUTER && x >= keep_x0 && x < keep_x1) atomicSub(&sh.need_left, 1);
             }
             __syncwarp();
-            { STAT_T0(); if (lane == 0) st_release(&V.pstate[pn], (K << 2) | 3u); __syncwarp(); STAT_T1(c_rel); }
+            { STAT_T0(); if (lane == 0) { st_release(&V.pstate[pn], (K << 2) | 3u); atomicAdd(&sh.done_t, 1); } __syncwarp(); STAT_T1(c_rel); }
             STAT_ADD(c_pop);
         }
         __syncthreads();
         if (tid == 0) {
-            sh.gbase = gbase + ncur; sh.npool = carry + ntask; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.tmin = 0xffffffffu;
+            sh.gbase = gbase + ncur; sh.npool = carry + ntask; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.done_t = 0; sh.tmin = 0xffffffffu;
         }
         src ^= 1;
         __syncthreads();
