@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
         if (lane == 0) h0[r] = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
     }
     // columns / rows of the tile window that lie inside the image
-    unsigned long long cm = 0;
-    for (int i = 0; i < 42; i++) { const int x = X0 - 5 + i; if (x >= 0 && x < a.Ws) cm |= 1ull << i; }
+    const int clo = max(0, 5 - X0), chi = min(42, a.Ws - (X0 - 5));      // bits [clo, chi) are image columns
+    const unsigned long long cm = ((1ull << chi) - 1ull) & ~((1ull << clo) - 1ull);
     __syncthreads();
     if (tid < 42) {
         const int r = tid, y = Y0 - 5 + r;
@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
         const int t4y = tid >> 2, t4x = tid & 3;
         const int ty = blockIdx.y * 4 + t4y, tx = blockIdx.x * 4 + t4x;
         if (ty < a.th && tx < a.tw) {
-            unsigned long long keep = 0;
-            for (int i = 0; i < 8; i++) { const int x = X0 + 8 * t4x + i; if (x >= a.keep_x0[v] && x < a.keep_x1[v]) keep |= 1ull << i; }
+            const int klo = min(8, max(0, a.keep_x0[v] - (X0 + 8 * t4x))), khi = max(0, min(8, a.keep_x1[v] - (X0 + 8 * t4x)));
+            const unsigned long long keep = khi > klo ? (((1ull << khi) - 1ull) & ~((1ull << klo) - 1ull)) : 0ull;
             int cnt = 0, need = 0;     // need = number of M pixels inside the kept window
             for (int i = 0; i < 8; i++) {
                 const int r = 5 + 8 * t4y + i, sh = 5 + 8 * t4x;
