@@ -421,7 +421,7 @@ static void prof_end(Slot& s) {
 
 // ---- device-level stage launchers (all asynchronous on s.stream) --------------------------------
 static int run_lanczos_rgb(Slot& s, const uint8_t* d_rgb, int H, int W, int SW, uint8_t* d_out) {
-    const int stage = (int)align_up((size_t)W * 3 + 16, 16);
+    const int stage = (int)align_up((size_t)W * 3 + 32, 16);
     const size_t smem = stage + align_up((size_t)SW * 3 + 16, 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "frame width %d too large for the row-staged Lanczos kernel", W);
     prof_begin(s, "lanczos_rgb_kernel");

@@ -136,4 +136,37 @@ __device__ __forceinline__ float det_powf(float x, float g) {
     return (float)det_exp2(__dmul_rn((double)g, det_log2((double)x)));
 }
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D) of a byte range into shared memory ---------------------
+// Rows of the frame are staged with the Blackwell copy engine instead of LSU loads: one elected
+// thread arms an mbarrier with the byte count and issues the bulk copy, the CTA waits on the barrier.
+// The engine needs 16-byte aligned addresses and sizes, so the copy starts at the enclosing aligned
+// address and the caller reads at `smem + (g & 15)` (the same convention as cta_copy_g2s).  Up to 15
+// bytes beyond the range are read: callers use the LSU path for the last row of a buffer.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned phase) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_addr(mbar)), "r"(phase) : "memory");
+    } while (!done);
+}
+// bytes the engine moves for the range [g, g+n): from the enclosing aligned address, rounded up to 16
+__device__ __forceinline__ unsigned tma_span(const uint8_t* g, int n) {
+    return (unsigned)((((uintptr_t)g & 15) + (unsigned)n + 15u) & ~15u);
+}
+// one thread: announce the total byte count of the copies that will complete on `mbar` (single arrival)
+__device__ __forceinline__ void tma_expect(unsigned long long* mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+}
+// one thread: copy [g & ~15, roundup16(g + n)) to smem_base (16-byte aligned); completion is signalled on mbar
+__device__ __forceinline__ void tma_copy_g2s(uint8_t* smem_base, const uint8_t* g, int n, unsigned long long* mbar) {
+    const uint8_t* ga = reinterpret_cast<const uint8_t*>((uintptr_t)g & ~(uintptr_t)15);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_base)), "l"(ga), "r"(tma_span(g, n)), "r"(smem_addr(mbar)) : "memory");
+}
+
 }  // namespace vsc
