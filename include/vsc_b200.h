@@ -162,6 +162,8 @@ int vsc_debug_fetch(vsc_ctx *ctx, int which, void *dst, size_t bytes);
 int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, size_t n);
 /* 64 phase counters of the hole-filling march (non-zero only in -DVSC_TELEA_STATS profiling builds) */
 int vsc_debug_telea_stats(vsc_ctx *ctx, unsigned long long *out64);
+/* test hook: set the hole-filling queue capacity (entries per view) to exercise the overflow/re-run path */
+int vsc_debug_set_telea_capacity(vsc_ctx *ctx, size_t entries);
 
 #ifdef __cplusplus
 }

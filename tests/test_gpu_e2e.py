@@ -100,6 +100,24 @@ def test_async_slots_match_sync(gen):
         assert np.array_equal(a, b)
 
 
+def test_queue_scratch_overflow_is_detected_and_rerun():
+    """The march's queue scratch is sized optimistically; a frame that needs more must be re-run with a larger
+    scratch and still be exact (vsc_wait), also through the asynchronous slots."""
+    g = StereoGenerator('cuda', n_slots=2)
+    try:
+        lib = _lib.load()
+        kw = dict(edge_softness=0.0, depth_gamma=1.0, super_sampling=2.0, max_disparity=60.0)
+        rgb, depth = make_pair(120, 200, seed=21)
+        ref = O.process_frame(rgb, depth, O.Params(**kw))
+        _lib.check(lib.vsc_debug_set_telea_capacity(g._ctx.handle, 64))
+        assert np.array_equal(g.process_frame(rgb, depth, StereoParams(**kw)), ref)
+        _lib.check(lib.vsc_debug_set_telea_capacity(g._ctx.handle, 64))
+        outs = g.process_batch([(rgb, depth)] * 3, StereoParams(**kw))
+        assert all(np.array_equal(o, ref) for o in outs)
+    finally:
+        g.close()
+
+
 def test_ready_and_wait_any(gen):
     frames = [make_pair(90, 160, seed=s) for s in range(5)]
     ref = [gen.process_frame(r, d) for r, d in frames]

@@ -525,7 +525,7 @@ static int ensure_telea(Slot& s, int Hs, int Ws, int nviews) {
     const int tw = (Ws + TG - 1) / TG, th = (Hs + TG - 1) / TG;
     const size_t nt = (size_t)tw * th;
     if (s.qcap == 0) s.qcap = npx / 8 > (1u << 20) ? npx / 8 : (1u << 20);
-    if (s.qcap > npx) s.qcap = npx;
+    if (s.qcap > npx + 1024) s.qcap = npx + 1024;
     for (int v = 0; v < nviews; v++) {
         int rc = 0;
         rc |= s.st[v].ensure(npx);
@@ -1105,5 +1105,19 @@ extern "C" int vsc_debug_telea_stats(vsc_ctx* ctx, unsigned long long* out64) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
     if (s.tstats.p) CU(cudaMemcpy(out64, s.tstats.p, 64 * 8, cudaMemcpyDeviceToHost));
+    return VSC_OK;
+}
+
+// test hook: shrink the hole-filling queue scratch of every slot so that the overflow -> regrow -> re-run path
+// (vsc_wait / vsc_stage_inpaint) can be exercised
+extern "C" int vsc_debug_set_telea_capacity(vsc_ctx* ctx, size_t entries) {
+    if (!ctx) return fail(VSC_E_INVALID, "null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    for (auto& s : ctx->slots) {
+        if (s.busy) return fail(VSC_E_STATE, "a slot is busy");
+        for (int v = 0; v < 2; v++) { s.qkey[v].release(); s.qidx[v].release(); }
+        s.qcap = entries;
+    }
     return VSC_OK;
 }
