@@ -109,50 +109,65 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     params = StereoParams()
-    slots, batch = args.slots, args.batch
-    gen = StereoGenerator(f'cuda:{local_rank}', n_slots=slots)
+    slots, batch, group = args.slots, args.batch, args.group
+    gen = StereoGenerator(f'cuda:{local_rank}', n_slots=slots, group_size=group)
     # distinct frames per rank (frame-range shard of the synthetic clip)
     n_distinct = min(N_DISTINCT, max(batch, slots))
     frames = make_frames(n_distinct, H, W, DEPTH_DTYPE, seed0=rank * 1000)
     d_rgb = [torch.from_numpy(r).cuda() for r, _ in frames]
     d_dep = [torch.from_numpy(d).cuda() for _, d in frames]
-    d_out = [torch.empty((H, 2 * W, 3), dtype=torch.uint8, device='cuda') for _ in range(slots)]
+    d_out = [[torch.empty((H, 2 * W, 3), dtype=torch.uint8, device='cuda') for _ in range(group)] for _ in range(slots)]
     torch.cuda.synchronize()
 
     def device_step(step):
-        """one batch, inputs resident in HBM; a finished slot is reused at once (no head-of-line blocking)"""
+        """one batch, inputs resident in HBM; a finished slot is reused at once (no head-of-line blocking);
+        every submission carries `group` frames that share the slot's stream and one hole-filling launch"""
         free, busy = list(range(slots)), []
-        for i in range(batch):
+        for i0 in range(0, batch, group):
             if not free:
                 s = gen.wait_any(busy)
                 gen.wait(s)
                 busy.remove(s)
                 free.append(s)
             s = free.pop(0)
-            f = (step * batch + i) % n_distinct
-            gen.submit_device(s, d_rgb[f].data_ptr(), d_dep[f].data_ptr(), DEPTH_DTYPE, H, W, d_out[s].data_ptr(), params)
+            tri = []
+            for k in range(min(group, batch - i0)):
+                f = (step * batch + i0 + k) % n_distinct
+                tri.append((d_rgb[f].data_ptr(), d_dep[f].data_ptr(), d_out[s][k].data_ptr()))
+            gen.submit_device_group(s, tri, DEPTH_DTYPE, H, W, params)
             busy.append(s)
         for s in busy:
             gen.wait(s)
 
+    from concurrent.futures import ThreadPoolExecutor
+    loaders = ThreadPoolExecutor(max_workers=max(1, group))
+    for s_ in range(slots):          # allocate the pinned staging buffers outside the timed region
+        for k_ in range(group):
+            gen.pinned_inputs(s_, H, W, DEPTH_DTYPE, k_)
+
     def e2e_step(step):
         free, busy, last = list(range(slots)), [], None
-        for i in range(batch):
+        for i0 in range(0, batch, group):
             if not free:
                 s = gen.wait_any(busy)
                 last = gen.collect(s, copy=False)
                 busy.remove(s)
                 free.append(s)
             s = free.pop(0)
-            f = (step * batch + i) % n_distinct
-            prgb, pdep = gen.pinned_inputs(s, H, W, DEPTH_DTYPE)
-            # the loader's job: decode straight into the slot's pinned buffers (here: memcpy of a prepared frame)
-            np.copyto(prgb, frames[f][0])
-            np.copyto(pdep, frames[f][1])
-            gen.submit_pinned(s, params)
+            n = min(group, batch - i0)
+
+            def load(k, s=s, i0=i0):
+                # the loader pool's job: decode straight into the slot's pinned buffers (here: memcpy of a prepared frame)
+                f = (step * batch + i0 + k) % n_distinct
+                prgb, pdep = gen.pinned_inputs(s, H, W, DEPTH_DTYPE, k)
+                np.copyto(prgb, frames[f][0])
+                np.copyto(pdep, frames[f][1])
+            list(loaders.map(load, range(n)))
+            gen.submit_pinned(s, params, n)
             busy.append(s)
         for s in busy:
             last = gen.collect(s, copy=False)
+        last = last[-1] if isinstance(last, list) else last
         return int(last[0, 0, 0])      # device->host read of the step's result
 
     def barrier():
@@ -177,7 +192,7 @@ def run_ours(args, rank, world, local_rank):
 
     for k in range(args.warmup):
         device_step(k)
-    launches_per_frame = gen.last_frame_launches(0)
+    launches_per_frame = gen.last_frame_launches(0) / group
     with ClockSampler(local_rank) as clk:
         ms_dev, wall_dev = timed(device_step, args.steps)
     for k in range(max(1, args.warmup // 2)):
@@ -191,7 +206,7 @@ def run_ours(args, rank, world, local_rank):
         nprof = 8
         for i in range(nprof):
             gen.submit_device(0, d_rgb[i % n_distinct].data_ptr(), d_dep[i % n_distinct].data_ptr(), DEPTH_DTYPE, H, W,
-                              d_out[0].data_ptr(), params)
+                              d_out[0][0].data_ptr(), params)
             gen.wait(0)
             if i >= 2:
                 per = {}
@@ -221,13 +236,13 @@ def run_ours(args, rank, world, local_rank):
             'metric': 'SBS frames/sec (1080p, default stereo params)', 'value': frames_total / (ms_dev * 1e-3), 'unit': 'frames/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': batch, 'slots_in_flight': slots,
+            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': batch, 'slots_in_flight': slots, 'frames_per_slot': group,
                        'distinct_frames': n_distinct, 'l2_policy': 'inputs larger than L2 (%d distinct frames cycled)' % n_distinct,
                        'sharding': 'frame-range, no collective'},
             'e2e': {'value': frames_total / (ms_e2e * 1e-3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': batch * (H * W * 3 + H * W * np.dtype(DEPTH_DTYPE).itemsize),
                     'd2h_bytes_per_step': batch * H * 2 * W * 3, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches_per_frame * batch * args.steps,
+            'gpu_launches': int(round(launches_per_frame * batch * args.steps)),
             'launches_per_frame': launches_per_frame,
             'clocks': clk.summary(),
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -310,7 +325,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=96, help='frames per step per GPU')
-    ap.add_argument('--slots', type=int, default=30, help='frames in flight per GPU')
+    ap.add_argument('--slots', type=int, default=30, help='slots (CUDA streams) per GPU')
+    ap.add_argument('--group', type=int, default=4, help='frames per slot submission (share a stream and one hole-filling launch)')
     ap.add_argument('--cpu-frames', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

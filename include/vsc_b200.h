@@ -73,6 +73,11 @@ int vsc_abi_version(void);
 const char *vsc_last_error(void);
 void vsc_default_params(vsc_params *p);                       /* StereoParams() defaults :196-202 */
 int vsc_create(int device, int n_slots, vsc_ctx **out);       /* n_slots frames may be in flight */
+/* Grouped context: every slot takes up to `group_size` (<= 4) frames per submission.  The frames of a slot
+ * share its CUDA stream and one hole-filling launch, so that n_slots * group_size frames overlap although the
+ * device offers only 32 hardware queues.  vsc_create == group_size 1. */
+int vsc_create_grouped(int device, int n_slots, int group_size, vsc_ctx **out);
+int vsc_group_size(const vsc_ctx *ctx);
 void vsc_destroy(vsc_ctx *ctx);
 int vsc_device(const vsc_ctx *ctx);
 int vsc_num_slots(const vsc_ctx *ctx);
@@ -94,6 +99,11 @@ int vsc_host_free(void *p);
  * should be pinned) until vsc_wait(slot) returns. */
 int vsc_submit(vsc_ctx *ctx, int slot, const uint8_t *rgb, const void *depth, int depth_dtype,
                int height, int width, const vsc_params *p, uint8_t *out_sbs);
+/* group variants: n (<= group_size) frames of identical size and parameters per submission */
+int vsc_submit_group(vsc_ctx *ctx, int slot, int n, const uint8_t *const *rgb, const void *const *depth, int depth_dtype,
+                     int height, int width, const vsc_params *p, uint8_t *const *out_sbs);
+int vsc_submit_device_group(vsc_ctx *ctx, int slot, int n, const uint8_t *const *d_rgb, const void *const *d_depth,
+                            int depth_dtype, int height, int width, const vsc_params *p, uint8_t *const *d_out_sbs);
 int vsc_wait(vsc_ctx *ctx, int slot);
 /* non-blocking: 1 if the slot's frame has finished (vsc_wait will not block), 0 if it is still running */
 int vsc_query(vsc_ctx *ctx, int slot);

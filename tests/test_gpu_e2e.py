@@ -118,6 +118,30 @@ def test_queue_scratch_overflow_is_detected_and_rerun():
         g.close()
 
 
+def test_grouped_slots_match_single_frames():
+    """Slots that take several frames per submission (shared stream, one hole-filling launch for all of them)
+    must give exactly the single-frame results, for full and partial groups and for mixed sizes."""
+    frames = [make_pair(90, 160, seed=s, depth_dtype=np.uint16) for s in range(8)] + [make_pair(72, 128, seed=40)]
+    single = StereoGenerator('cuda', n_slots=1)
+    ref = [single.process_frame(r, d) for r, d in frames]
+    single.close()
+    g = StereoGenerator('cuda', n_slots=2, group_size=3)
+    try:
+        outs = g.process_batch(frames)
+        assert len(outs) == len(ref)
+        for a, b in zip(outs, ref):
+            assert np.array_equal(a, b)
+        g.submit_frames(0, frames[:2])
+        g.submit_frames(1, frames[2:5])
+        r1, r0 = g.collect(1), g.collect(0)
+        assert all(np.array_equal(a, b) for a, b in zip(r0 + r1, ref[:5]))
+        assert np.array_equal(g.process_frame(*frames[5]), ref[5])
+        with pytest.raises(ValueError):
+            g.submit_frames(0, frames[:4])
+    finally:
+        g.close()
+
+
 def test_ready_and_wait_any(gen):
     frames = [make_pair(90, 160, seed=s) for s in range(5)]
     ref = [gen.process_frame(r, d) for r, d in frames]

@@ -233,7 +233,9 @@ struct DevBuf {
 };
 
 struct Slot {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // shared by the slots of one group (the group leader owns it)
+    bool owns_stream = false;
+    int nfr = 0;                         // leader only: frames in the group's current submission
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // inputs / outputs staged on device for host-buffer submissions
     DevBuf in_rgb, in_depth, out_sbs;
@@ -264,6 +266,7 @@ struct Slot {
 
 struct vsc_ctx {
     int device = 0;
+    int group_size = 1;                  // frames that share one stream and one hole-filling launch
     bool profiling = false;
     cudaStream_t tstream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -308,10 +311,11 @@ static int set_smem_attrs() {
     return VSC_OK;
 }
 
-extern "C" int vsc_create(int device, int n_slots, vsc_ctx** out) {
+extern "C" int vsc_create_grouped(int device, int n_groups, int group_size, vsc_ctx** out) {
     if (!out) return fail(VSC_E_INVALID, "null out pointer");
     *out = nullptr;
-    if (n_slots < 1 || n_slots > 64) return fail(VSC_E_INVALID, "n_slots must be in [1,64]");
+    if (n_groups < 1 || n_groups > 64) return fail(VSC_E_INVALID, "number of slots must be in [1,64]");
+    if (group_size < 1 || group_size > TELEA_MAX_VIEWS / 2) return fail(VSC_E_INVALID, "group size must be in [1,%d]", TELEA_MAX_VIEWS / 2);
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // one hardware queue per slot stream (no effect once a context exists)
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -322,15 +326,24 @@ extern "C" int vsc_create(int device, int n_slots, vsc_ctx** out) {
     CU(cudaSetDevice(device));
     vsc_ctx* ctx = new vsc_ctx();
     ctx->device = device;
+    ctx->group_size = group_size;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = set_smem_attrs();
     if (rc == VSC_OK) rc = upload_constants(ctx);
     if (rc != VSC_OK) { delete ctx; return rc; }
-    ctx->slots.resize(n_slots);
-    for (auto& s : ctx->slots) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreate(&s.ev0) != cudaSuccess || cudaEventCreate(&s.ev1) != cudaSuccess ||
-            cudaMallocHost((void**)&s.h_scalars, sizeof(FrameScalars)) != cudaSuccess) {
+    ctx->slots.resize((size_t)n_groups * group_size);
+    for (size_t i = 0; i < ctx->slots.size(); i++) {
+        Slot& s = ctx->slots[i];
+        bool ok = true;
+        if (i % group_size == 0) {
+            ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+            s.owns_stream = ok;
+        } else {
+            s.stream = ctx->slots[i - i % group_size].stream;
+        }
+        ok = ok && cudaEventCreate(&s.ev0) == cudaSuccess && cudaEventCreate(&s.ev1) == cudaSuccess &&
+             cudaMallocHost((void**)&s.h_scalars, sizeof(FrameScalars)) == cudaSuccess;
+        if (!ok) {
             vsc_destroy(ctx);
             return fail(VSC_E_CUDA, "failed to create stream/events for a slot");
         }
@@ -339,6 +352,8 @@ extern "C" int vsc_create(int device, int n_slots, vsc_ctx** out) {
     *out = ctx;
     return VSC_OK;
 }
+extern "C" int vsc_create(int device, int n_slots, vsc_ctx** out) { return vsc_create_grouped(device, n_slots, 1, out); }
+extern "C" int vsc_group_size(const vsc_ctx* ctx) { return ctx ? ctx->group_size : 0; }
 
 extern "C" void vsc_destroy(vsc_ctx* ctx) {
     if (!ctx) return;
@@ -353,13 +368,13 @@ extern "C" void vsc_destroy(vsc_ctx* ctx) {
         if (s.h_scalars) cudaFreeHost(s.h_scalars);
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
-        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.stream && s.owns_stream) cudaStreamDestroy(s.stream);
     }
     ctx->color_w.release();
     delete ctx;
 }
 extern "C" int vsc_device(const vsc_ctx* ctx) { return ctx ? ctx->device : -1; }
-extern "C" int vsc_num_slots(const vsc_ctx* ctx) { return ctx ? (int)ctx->slots.size() : 0; }
+extern "C" int vsc_num_slots(const vsc_ctx* ctx) { return ctx ? (int)(ctx->slots.size() / ctx->group_size) : 0; }
 extern "C" int vsc_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(VSC_E_INVALID, "null out pointer");
     CU(cudaMallocHost(out, bytes));
@@ -539,15 +554,20 @@ static int ensure_telea(Slot& s, int Hs, int Ws, int nviews) {
     }
     return VSC_OK;
 }
-static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4* img1, const uint8_t* valid0,
-                     const uint8_t* valid1, int k0a, int k1a, int k0b, int k1b, int nviews) {
-    int rc = ensure_telea(s, Hs, Ws, nviews);
-    if (rc) return rc;
+struct ViewSpec {       // one eye of one frame for the hole-filling launch
+    Slot* fr;           // the frame slot that owns the scratch buffers and the frame scalars
+    int b;              // 0 = left, 1 = right
+    uchar4* img;
+    const uint8_t* valid;
+    int k0, k1;         // columns the back end reads
+};
+// `s` is the group leader (stream, launch / profiling bookkeeping); the views may belong to several frame slots
+static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, int nviews) {
+    if (nviews < 1 || nviews > TELEA_MAX_VIEWS) return fail(VSC_E_INVALID, "bad view count");
+    for (int v = 0; v < nviews; v++) { int rc = ensure_telea(*vs[v].fr, Hs, Ws, 2); if (rc) return rc; }
     TeleaArgs a;
     memset(&a, 0, sizeof a);
-    a.fs = s.scalars.as<FrameScalars>();
     a.Hs = Hs; a.Ws = Ws; a.tw = (Ws + TG - 1) / TG; a.th = (Hs + TG - 1) / TG;
-    a.keep_x0[0] = k0a; a.keep_x1[0] = k1a; a.keep_x0[1] = k0b; a.keep_x1[1] = k1b;
     a.nviews = nviews;
 #ifdef VSC_TELEA_STATS
     if (s.tstats.ensure(64 * 8)) return VSC_E_NOMEM;
@@ -555,24 +575,26 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, uchar4* img0, uchar4
     a.stats = s.tstats.as<unsigned long long>();
 #endif
     const size_t nt = (size_t)a.tw * a.th;
-    uchar4* imgs[2] = {img0, img1};
-    const uint8_t* valids[2] = {valid0, valid1};
-    for (int v = 0; v < 2; v++) {
-        const int b = v < nviews ? v : 0;
+    for (int v = 0; v < nviews; v++) {
+        Slot& f = *vs[v].fr;
+        const int b = vs[v].b;
         TeleaView& V = a.v[v];
-        V.img = imgs[b]; V.valid = valids[b];
-        V.st = s.st[b].as<uint8_t>(); V.tt = s.tt[b].as<float>();
-        V.tile_cnt = s.tile_u8[b].as<unsigned char>(); V.tile_need = V.tile_cnt + nt;
-        int* ib = s.tile_i32[b].as<int>();
+        V.img = vs[v].img; V.valid = vs[v].valid;
+        V.st = f.st[b].as<uint8_t>(); V.tt = f.tt[b].as<float>();
+        V.tile_cnt = f.tile_u8[b].as<unsigned char>(); V.tile_need = V.tile_cnt + nt;
+        int* ib = f.tile_i32[b].as<int>();
         V.lab = ib; V.csize = ib + nt; V.ctiles = ib + 2 * nt; V.cneed = ib + 3 * nt; V.cslot = ib + 4 * nt;
         V.cl_qoff = ib + 5 * nt; V.cl_toff = ib + 6 * nt; V.cl_ntiles = ib + 7 * nt; V.cl_size = ib + 8 * nt;
         V.cl_fill = ib + 9 * nt; V.tile_list = ib + 10 * nt;
-        V.qkey[0] = s.qkey[b].as<unsigned long long>(); V.qkey[1] = V.qkey[0] + s.qcap; V.qkey[2] = V.qkey[1] + s.qcap;
-        V.qidx[0] = s.qidx[b].as<unsigned>(); V.qidx[1] = V.qidx[0] + s.qcap; V.qidx[2] = V.qidx[1] + s.qcap;
-        V.pstate = s.pstate[b].as<unsigned>();
-        V.qcap = (int)s.qcap;
+        V.qkey[0] = f.qkey[b].as<unsigned long long>(); V.qkey[1] = V.qkey[0] + f.qcap; V.qkey[2] = V.qkey[1] + f.qcap;
+        V.qidx[0] = f.qidx[b].as<unsigned>(); V.qidx[1] = V.qidx[0] + f.qcap; V.qidx[2] = V.qidx[1] + f.qcap;
+        V.pstate = f.pstate[b].as<unsigned>();
+        V.qcap = (int)f.qcap;
+        V.fs = f.scalars.as<FrameScalars>();
+        V.vi = b;
+        V.keep_x0 = vs[v].k0; V.keep_x1 = vs[v].k1;
+        CU(cudaMemsetAsync(f.pstate[b].p, 0xff, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'task done'
     }
-    for (int v = 0; v < nviews; v++) CU(cudaMemsetAsync(s.pstate[v].p, 0xff, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'task done'
     dim3 pgrid((Ws + 31) / 32, (Hs + 31) / 32, nviews), pblock(32, 8);
     prof_begin(s, "telea_prepare_kernel");
     telea_prepare_kernel<<<pgrid, pblock, 0, s.stream>>>(a);
@@ -633,113 +655,153 @@ static int ensure_frame_buffers(Slot& s, const vsc_geom& g, bool smoothing) {
     return rc ? VSC_E_NOMEM : VSC_OK;
 }
 
-static int enqueue_frame(vsc_ctx* ctx, Slot& s, const uint8_t* d_rgb, const void* d_depth, int dtype, const vsc_geom& g,
-                         const vsc_params& p, uint8_t* d_out) {
+// Enqueue n frames of one group (slot) on the group's stream.  Every frame runs its own wide kernels; the
+// hole filling of all frames is ONE launch sequence, so that the latency-bound march of up to
+// group_size frames overlaps on a single stream.  `fr` points at the group's first frame slot (the leader).
+static int enqueue_group(vsc_ctx* ctx, Slot* fr, int n, int dtype, const vsc_geom& g, const vsc_params& p) {
+    Slot& lead = fr[0];
     const bool smoothing = p.artifact_smoothing > 0;
-    int rc = ensure_frame_buffers(s, g, smoothing);
-    if (rc) return rc;
-    rc = ensure_tables(s, g);
-    if (rc) return rc;
-    s.launches = 0;
-    s.pcount = 0;
-    CU(cudaEventRecord(s.ev0, s.stream));
-    prof_begin(s, "frame_init_kernel");
-    frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
-    KCHECK(s);
-    if ((rc = run_lanczos_rgb(s, d_rgb, g.height, g.width, g.stretched_w, s.rgb_st.as<uint8_t>()))) return rc;
-    if ((rc = run_lanczos_depth(s, d_depth, dtype, g.height, g.width, g.stretched_w, s.depth_st.as<float>()))) return rc;
-    if ((rc = run_depth_front(ctx, s, g, p, s.depth_st.as<float>(), s.depth_ss.as<float>()))) return rc;
-    uchar4* va[2] = {s.viewA[0].as<uchar4>(), s.viewA[1].as<uchar4>()};
-    uint8_t* vm[2] = {s.vmask[0].as<uint8_t>(), s.vmask[1].as<uint8_t>()};
-    if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 0))) return rc;
-    uchar4* cur[2] = {va[0], va[1]};
-    if (smoothing) {
-        // `if image_np.max() > 1.0 ... else (image_np * 255)` (stereo_core.py:404-407): conditional re-run on device
-        if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 1))) return rc;
-        uchar4* vb[2] = {s.viewB[0].as<uchar4>(), s.viewB[1].as<uchar4>()};
-        if ((rc = run_bilateral(ctx, s, g.ss_h, g.ss_w, p.artifact_smoothing, va[0], va[1], vb[0], vb[1], 2))) return rc;
-        cur[0] = vb[0]; cur[1] = vb[1];
+    for (int i = 0; i < n; i++) {
+        int rc = ensure_frame_buffers(fr[i], g, smoothing);
+        if (!rc) rc = ensure_tables(fr[i], g);
+        if (rc) return rc;
+        fr[i].launches = 0;
+        fr[i].pcount = 0;
     }
-    if ((rc = run_telea(ctx, s, g.ss_h, g.ss_w, cur[0], cur[1], vm[0], vm[1], g.left_crop, g.left_crop + g.crop_w,
-                        g.right_crop, g.right_crop + g.crop_w, 2))) return rc;
-    if ((rc = run_backend(s, g, p.sharpen, cur[0], cur[1], d_out))) return rc;
-    CU(cudaEventRecord(s.ev1, s.stream));
-    CU(cudaMemcpyAsync(s.h_scalars, s.scalars.p, sizeof(FrameScalars), cudaMemcpyDeviceToHost, s.stream));
-    return VSC_OK;
-}
-
-static int check_args(vsc_ctx* ctx, int slot, const void* rgb, const void* depth, int dtype, const vsc_params* p, void* out) {
-    if (!ctx) return fail(VSC_E_INVALID, "null context");
-    if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "slot %d out of range", slot);
-    if (!rgb || !depth || !p || !out) return fail(VSC_E_INVALID, "null buffer");
-    if (dtype != VSC_DEPTH_U8 && dtype != VSC_DEPTH_U16 && dtype != VSC_DEPTH_F32) return fail(VSC_E_INVALID, "unsupported depth dtype %d", dtype);
-    return VSC_OK;
-}
-
-static int submit_impl(vsc_ctx* ctx, int slot, const uint8_t* rgb, const void* depth, int dtype, int H, int W,
-                       const vsc_params* p, uint8_t* out, bool device_io) {
-    int rc = check_args(ctx, slot, rgb, depth, dtype, p, out);
+    CU(cudaEventRecord(lead.ev0, lead.stream));
+    ViewSpec vs[TELEA_MAX_VIEWS];
+    uchar4* cur[TELEA_MAX_VIEWS];
+    for (int i = 0; i < n; i++) {
+        Slot& s = fr[i];
+        int rc;
+        prof_begin(s, "frame_init_kernel");
+        frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
+        KCHECK(s);
+        if ((rc = run_lanczos_rgb(s, s.l_rgb, g.height, g.width, g.stretched_w, s.rgb_st.as<uint8_t>()))) return rc;
+        if ((rc = run_lanczos_depth(s, s.l_depth, dtype, g.height, g.width, g.stretched_w, s.depth_st.as<float>()))) return rc;
+        if ((rc = run_depth_front(ctx, s, g, p, s.depth_st.as<float>(), s.depth_ss.as<float>()))) return rc;
+        uchar4* va[2] = {s.viewA[0].as<uchar4>(), s.viewA[1].as<uchar4>()};
+        uint8_t* vm[2] = {s.vmask[0].as<uint8_t>(), s.vmask[1].as<uint8_t>()};
+        if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 0))) return rc;
+        cur[2 * i] = va[0]; cur[2 * i + 1] = va[1];
+        if (smoothing) {
+            // `if image_np.max() > 1.0 ... else (image_np * 255)` (stereo_core.py:404-407): conditional re-run on device
+            if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 1))) return rc;
+            uchar4* vb[2] = {s.viewB[0].as<uchar4>(), s.viewB[1].as<uchar4>()};
+            if ((rc = run_bilateral(ctx, s, g.ss_h, g.ss_w, p.artifact_smoothing, va[0], va[1], vb[0], vb[1], 2))) return rc;
+            cur[2 * i] = vb[0]; cur[2 * i + 1] = vb[1];
+        }
+        vs[2 * i] = ViewSpec{&s, 0, cur[2 * i], vm[0], g.left_crop, g.left_crop + g.crop_w};
+        vs[2 * i + 1] = ViewSpec{&s, 1, cur[2 * i + 1], vm[1], g.right_crop, g.right_crop + g.crop_w};
+    }
+    int rc = run_telea(ctx, lead, g.ss_h, g.ss_w, vs, 2 * n);
     if (rc) return rc;
-    Slot& s = ctx->slots[slot];
-    if (s.busy) return fail(VSC_E_STATE, "slot %d still has a frame in flight; call vsc_wait first", slot);
+    for (int i = 0; i < n; i++)
+        if ((rc = run_backend(fr[i], g, p.sharpen, cur[2 * i], cur[2 * i + 1], fr[i].l_out))) return rc;
+    CU(cudaEventRecord(lead.ev1, lead.stream));
+    for (int i = 0; i < n; i++)
+        CU(cudaMemcpyAsync(fr[i].h_scalars, fr[i].scalars.p, sizeof(FrameScalars), cudaMemcpyDeviceToHost, lead.stream));
+    return VSC_OK;
+}
+
+static int submit_group_impl(vsc_ctx* ctx, int slot, int n, const uint8_t* const* rgb, const void* const* depth, int dtype,
+                             int H, int W, const vsc_params* p, uint8_t* const* out, bool device_io) {
+    if (!ctx) return fail(VSC_E_INVALID, "null context");
+    const int G = ctx->group_size;
+    if (slot < 0 || slot >= (int)ctx->slots.size() / G) return fail(VSC_E_INVALID, "slot %d out of range", slot);
+    if (n < 1 || n > G) return fail(VSC_E_INVALID, "a slot of this context takes 1..%d frames per submission", G);
+    if (!rgb || !depth || !p || !out) return fail(VSC_E_INVALID, "null buffer");
+    for (int i = 0; i < n; i++) if (!rgb[i] || !depth[i] || !out[i]) return fail(VSC_E_INVALID, "null buffer");
+    if (dtype != VSC_DEPTH_U8 && dtype != VSC_DEPTH_U16 && dtype != VSC_DEPTH_F32) return fail(VSC_E_INVALID, "unsupported depth dtype %d", dtype);
+    Slot* fr = &ctx->slots[(size_t)slot * G];
+    Slot& lead = fr[0];
+    if (lead.busy) return fail(VSC_E_STATE, "slot %d still has frames in flight; call vsc_wait first", slot);
     vsc_geom g;
+    int rc;
     if ((rc = vsc_geometry(H, W, p, &g))) return rc;
     CU(cudaSetDevice(ctx->device));
     const size_t nrgb = (size_t)H * W * 3, ndepth = (size_t)H * W * depth_elem(dtype), nout = (size_t)H * 2 * W * 3;
-    const uint8_t* d_rgb = rgb; const void* d_depth = depth; uint8_t* d_out = out;
-    if (!device_io) {
-        if (s.in_rgb.ensure(nrgb) || s.in_depth.ensure(ndepth) || s.out_sbs.ensure(nout)) return VSC_E_NOMEM;
-        CU(cudaMemcpyAsync(s.in_rgb.p, rgb, nrgb, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.in_depth.p, depth, ndepth, cudaMemcpyHostToDevice, s.stream));
-        d_rgb = s.in_rgb.as<uint8_t>(); d_depth = s.in_depth.p; d_out = s.out_sbs.as<uint8_t>();
+    for (int i = 0; i < n; i++) {
+        Slot& s = fr[i];
+        s.l_rgb = rgb[i]; s.l_depth = depth[i]; s.l_out = out[i]; s.l_host_out = nullptr; s.l_out_bytes = nout;
+        if (!device_io) {
+            if (s.in_rgb.ensure(nrgb) || s.in_depth.ensure(ndepth) || s.out_sbs.ensure(nout)) return VSC_E_NOMEM;
+            CU(cudaMemcpyAsync(s.in_rgb.p, rgb[i], nrgb, cudaMemcpyHostToDevice, lead.stream));
+            CU(cudaMemcpyAsync(s.in_depth.p, depth[i], ndepth, cudaMemcpyHostToDevice, lead.stream));
+            s.l_rgb = s.in_rgb.as<uint8_t>(); s.l_depth = s.in_depth.p; s.l_out = s.out_sbs.as<uint8_t>();
+            s.l_host_out = out[i];
+        }
     }
-    rc = enqueue_frame(ctx, s, d_rgb, d_depth, dtype, g, *p, d_out);
-    if (rc) { cudaStreamSynchronize(s.stream); return rc; }
-    if (!device_io) CU(cudaMemcpyAsync(out, d_out, nout, cudaMemcpyDeviceToHost, s.stream));
-    s.busy = true;
-    s.l_rgb = d_rgb; s.l_depth = d_depth; s.l_out = d_out; s.l_dtype = dtype; s.l_H = H; s.l_W = W; s.l_p = *p;
-    s.l_host_out = device_io ? nullptr : out; s.l_out_bytes = nout;
+    rc = enqueue_group(ctx, fr, n, dtype, g, *p);
+    if (rc) { cudaStreamSynchronize(lead.stream); return rc; }
+    for (int i = 0; i < n; i++)
+        if (fr[i].l_host_out) CU(cudaMemcpyAsync(fr[i].l_host_out, fr[i].l_out, nout, cudaMemcpyDeviceToHost, lead.stream));
+    lead.busy = true;
+    lead.nfr = n;
+    lead.l_dtype = dtype; lead.l_H = H; lead.l_W = W; lead.l_p = *p;
     return VSC_OK;
 }
 
+extern "C" int vsc_submit_group(vsc_ctx* ctx, int slot, int n, const uint8_t* const* rgb, const void* const* depth, int dtype,
+                                int H, int W, const vsc_params* p, uint8_t* const* out) {
+    return submit_group_impl(ctx, slot, n, rgb, depth, dtype, H, W, p, out, false);
+}
+extern "C" int vsc_submit_device_group(vsc_ctx* ctx, int slot, int n, const uint8_t* const* d_rgb, const void* const* d_depth,
+                                       int dtype, int H, int W, const vsc_params* p, uint8_t* const* d_out) {
+    return submit_group_impl(ctx, slot, n, d_rgb, d_depth, dtype, H, W, p, d_out, true);
+}
 extern "C" int vsc_submit(vsc_ctx* ctx, int slot, const uint8_t* rgb, const void* depth, int dtype, int H, int W,
                           const vsc_params* p, uint8_t* out) {
-    return submit_impl(ctx, slot, rgb, depth, dtype, H, W, p, out, false);
+    return submit_group_impl(ctx, slot, 1, &rgb, &depth, dtype, H, W, p, &out, false);
 }
 extern "C" int vsc_submit_device(vsc_ctx* ctx, int slot, const uint8_t* d_rgb, const void* d_depth, int dtype, int H, int W,
                                  const vsc_params* p, uint8_t* d_out) {
-    return submit_impl(ctx, slot, d_rgb, d_depth, dtype, H, W, p, d_out, true);
+    return submit_group_impl(ctx, slot, 1, &d_rgb, &d_depth, dtype, H, W, p, &d_out, true);
+}
+
+static Slot* group_lead(vsc_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() / ctx->group_size) return nullptr;
+    return &ctx->slots[(size_t)slot * ctx->group_size];
 }
 
 extern "C" int vsc_wait(vsc_ctx* ctx, int slot) {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad context or slot");
-    Slot& s = ctx->slots[slot];
-    if (!s.busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slot);
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr) return fail(VSC_E_INVALID, "bad context or slot");
+    Slot& lead = fr[0];
+    if (!lead.busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slot);
     CU(cudaSetDevice(ctx->device));
+    const int n = lead.nfr;
+    bool overflow = false;
     for (int attempt = 0; attempt < 4; attempt++) {
-        cudaError_t e = cudaStreamSynchronize(s.stream);
-        if (e != cudaSuccess) { s.busy = false; return fail(VSC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
-        if (s.h_scalars->overflow == 0) break;
-        // Telea queue scratch was too small for this frame's holes: grow and redo the frame
-        const size_t need = (size_t)s.h_scalars->overflow;
-        s.qcap = need + need / 4 + 1024;
+        cudaError_t e = cudaStreamSynchronize(lead.stream);
+        if (e != cudaSuccess) { lead.busy = false; return fail(VSC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
+        overflow = false;
+        for (int i = 0; i < n; i++)
+            if (fr[i].h_scalars->overflow) {
+                // Telea queue scratch was too small for this frame's holes: grow it and redo the submission
+                const size_t need = (size_t)fr[i].h_scalars->overflow;
+                fr[i].qcap = need + need / 4 + 1024;
+                overflow = true;
+            }
+        if (!overflow) break;
         vsc_geom g;
-        int rc = vsc_geometry(s.l_H, s.l_W, &s.l_p, &g);
-        if (!rc) rc = enqueue_frame(ctx, s, s.l_rgb, s.l_depth, s.l_dtype, g, s.l_p, s.l_out);
-        if (rc) { s.busy = false; return rc; }
-        if (s.l_host_out) CU(cudaMemcpyAsync(s.l_host_out, s.l_out, s.l_out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        int rc = vsc_geometry(lead.l_H, lead.l_W, &lead.l_p, &g);
+        if (!rc) rc = enqueue_group(ctx, fr, n, lead.l_dtype, g, lead.l_p);
+        if (rc) { lead.busy = false; return rc; }
+        for (int i = 0; i < n; i++)
+            if (fr[i].l_host_out) CU(cudaMemcpyAsync(fr[i].l_host_out, fr[i].l_out, fr[i].l_out_bytes, cudaMemcpyDeviceToHost, lead.stream));
     }
-    s.busy = false;
-    if (s.h_scalars->overflow) return fail(VSC_E_NOMEM, "hole-filling scratch overflow persisted");
-    cudaEventElapsedTime(&s.last_ms, s.ev0, s.ev1);
+    lead.busy = false;
+    if (overflow) return fail(VSC_E_NOMEM, "hole-filling scratch overflow persisted");
+    cudaEventElapsedTime(&lead.last_ms, lead.ev0, lead.ev1);
     return VSC_OK;
 }
 
 extern "C" int vsc_query(vsc_ctx* ctx, int slot) {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad context or slot");
-    Slot& s = ctx->slots[slot];
-    if (!s.busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slot);
-    cudaError_t e = cudaStreamQuery(s.stream);
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr) return fail(VSC_E_INVALID, "bad context or slot");
+    if (!fr->busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slot);
+    cudaError_t e = cudaStreamQuery(fr->stream);
     if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) return 0;
     return fail(VSC_E_CUDA, "stream query failed: %s", cudaGetErrorString(e));
@@ -748,22 +810,26 @@ extern "C" int vsc_query(vsc_ctx* ctx, int slot) {
 extern "C" int vsc_sync(vsc_ctx* ctx) {
     if (!ctx) return fail(VSC_E_INVALID, "null context");
     int rc = VSC_OK;
-    for (int i = 0; i < (int)ctx->slots.size(); i++)
-        if (ctx->slots[i].busy) { int r = vsc_wait(ctx, i); if (r) rc = r; }
+    for (int i = 0; i < (int)ctx->slots.size() / ctx->group_size; i++)
+        if (group_lead(ctx, i)->busy) { int r = vsc_wait(ctx, i); if (r) rc = r; }
     return rc;
 }
 extern "C" void* vsc_slot_stream(vsc_ctx* ctx, int slot) {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return nullptr;
-    return (void*)ctx->slots[slot].stream;
+    Slot* fr = group_lead(ctx, slot);
+    return fr ? (void*)fr->stream : nullptr;
 }
 extern "C" int vsc_slot_elapsed_ms(vsc_ctx* ctx, int slot, float* ms) {
-    if (!ctx || !ms || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad argument");
-    *ms = ctx->slots[slot].last_ms;
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr || !ms) return fail(VSC_E_INVALID, "bad argument");
+    *ms = fr->last_ms;
     return VSC_OK;
 }
 extern "C" int vsc_slot_launches(vsc_ctx* ctx, int slot) {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return -1;
-    return ctx->slots[slot].launches;
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr) return -1;
+    int total = 0;
+    for (int i = 0; i < ctx->group_size; i++) total += fr[i].launches;
+    return total;
 }
 
 extern "C" int vsc_process_frame(vsc_ctx* ctx, const uint8_t* rgb, const void* depth, int dtype, int H, int W,
@@ -942,8 +1008,8 @@ extern "C" int vsc_stage_inpaint(vsc_ctx* ctx, uint8_t* img, const uint8_t* vali
     CU(cudaMemcpyAsync(dval.p, valid, n, cudaMemcpyHostToDevice, s.stream));
     for (int attempt = 0; attempt < 4; attempt++) {
         frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
-        if ((rc = run_telea(ctx, s, H, W, (uchar4*)dimg.p, (uchar4*)dimg.p, (const uint8_t*)dval.p, (const uint8_t*)dval.p,
-                            keep_x0, keep_x0 + keep_w, keep_x0, keep_x0 + keep_w, 1))) return rc;
+        ViewSpec one{&s, 0, (uchar4*)dimg.p, (const uint8_t*)dval.p, keep_x0, keep_x0 + keep_w};
+        if ((rc = run_telea(ctx, s, H, W, &one, 1))) return rc;
         CU(cudaMemcpyAsync(s.h_scalars, s.scalars.p, sizeof(FrameScalars), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
         if (!s.h_scalars->overflow) break;
@@ -1059,12 +1125,15 @@ extern "C" int vsc_set_profiling(vsc_ctx* ctx, int on) {
 }
 // per-kernel device times of the last completed frame on `slot` (needs vsc_set_profiling(ctx,1) before submit)
 extern "C" int vsc_slot_kernel_times(vsc_ctx* ctx, int slot, int max_n, const char** names, float* ms) {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(VSC_E_INVALID, "bad argument");
-    Slot& s = ctx->slots[slot];
-    int n = s.pcount < max_n ? s.pcount : max_n;
-    for (int i = 0; i < n; i++) {
-        names[i] = s.pname[i];
-        if (cudaEventElapsedTime(&ms[i], s.pev[2 * i], s.pev[2 * i + 1]) != cudaSuccess) ms[i] = -1.f;
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr || !names || !ms) return fail(VSC_E_INVALID, "bad argument");
+    int n = 0;
+    for (int f = 0; f < ctx->group_size; f++) {
+        Slot& s = fr[f];
+        for (int i = 0; i < s.pcount && n < max_n; i++, n++) {
+            names[n] = s.pname[i];
+            if (cudaEventElapsedTime(&ms[n], s.pev[2 * i], s.pev[2 * i + 1]) != cudaSuccess) ms[n] = -1.f;
+        }
     }
     return n;
 }
@@ -1081,13 +1150,14 @@ extern "C" int vsc_timer_begin(vsc_ctx* ctx) {
     }
     CU(cudaDeviceSynchronize());
     CU(cudaEventRecord(ctx->t0, ctx->tstream));
-    for (auto& s : ctx->slots) CU(cudaStreamWaitEvent(s.stream, ctx->t0, 0));
+    for (auto& s : ctx->slots) if (s.owns_stream) CU(cudaStreamWaitEvent(s.stream, ctx->t0, 0));
     return VSC_OK;
 }
 extern "C" int vsc_timer_end(vsc_ctx* ctx, float* ms) {
     if (!ctx || !ms || !ctx->tstream) return fail(VSC_E_INVALID, "timer not started");
     CU(cudaSetDevice(ctx->device));
     for (size_t i = 0; i < ctx->slots.size(); i++) {
+        if (!ctx->slots[i].owns_stream) continue;
         CU(cudaEventRecord(ctx->tslot[i], ctx->slots[i].stream));
         CU(cudaStreamWaitEvent(ctx->tstream, ctx->tslot[i], 0));
     }

@@ -49,15 +49,17 @@ struct TeleaView {
     int* tile_list;            // [ntiles_active]
     unsigned long long* qkey[3];   // two ping-pong pools + the current generation
     unsigned* qidx[3];
-    unsigned* pstate;          // [Hs][Ws] (global pop index << 1) | done, for the dataflow order
+    unsigned* pstate;          // [Hs][Ws] order / completion word per pixel for the dataflow (see march)
     int qcap;
+    FrameScalars* fs;          // per-frame counters of the frame this view belongs to
+    int vi;                    // 0 = left, 1 = right eye within that frame
+    int keep_x0, keep_x1;      // columns the back end reads
 };
 
+constexpr int TELEA_MAX_VIEWS = 8;   // a march launch covers up to 4 frames x 2 eyes
 struct TeleaArgs {
-    TeleaView v[2];
-    FrameScalars* fs;
+    TeleaView v[TELEA_MAX_VIEWS];
     int Hs, Ws, tw, th;
-    int keep_x0[2], keep_x1[2];
     int nviews;
     unsigned long long* stats;   // optional [2 views][2 passes][16] counters (VSC_TELEA_STATS builds)
 };
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
         const int t4y = tid >> 2, t4x = tid & 3;
         const int ty = blockIdx.y * 4 + t4y, tx = blockIdx.x * 4 + t4x;
         if (ty < a.th && tx < a.tw) {
-            const int klo = min(8, max(0, a.keep_x0[v] - (X0 + 8 * t4x))), khi = max(0, min(8, a.keep_x1[v] - (X0 + 8 * t4x)));
+            const int klo = min(8, max(0, V.keep_x0 - (X0 + 8 * t4x))), khi = max(0, min(8, V.keep_x1 - (X0 + 8 * t4x)));
             const unsigned long long keep = khi > klo ? (((1ull << khi) - 1ull) & ~((1ull << klo) - 1ull)) : 0ull;
             int cnt = 0, need = 0;     // need = number of M pixels inside the kept window
             for (int i = 0; i < 8; i++) {
@@ -211,9 +213,9 @@ __global__ void telea_cluster_alloc_kernel(const __grid_constant__ TeleaArgs a) 
             if (V.lab[t] != t || !V.cneed[t]) continue;
             // big clusters get slots from the front, small ones from the back: the work queue starts the
             // long poles first
-            const int ci = V.csize[t] >= 1024 ? atomicAdd(&a.fs->nbig[v], 1) : n - 1 - atomicAdd(&a.fs->nsmall[v], 1);
-            V.cl_qoff[ci] = atomicAdd(&a.fs->qbump[v], V.csize[t]);
-            V.cl_toff[ci] = atomicAdd(&a.fs->tbump[v], V.ctiles[t]);
+            const int ci = V.csize[t] >= 1024 ? atomicAdd(&V.fs->nbig[V.vi], 1) : n - 1 - atomicAdd(&V.fs->nsmall[V.vi], 1);
+            V.cl_qoff[ci] = atomicAdd(&V.fs->qbump[V.vi], V.csize[t]);
+            V.cl_toff[ci] = atomicAdd(&V.fs->tbump[V.vi], V.ctiles[t]);
             V.cl_ntiles[ci] = V.ctiles[t];
             V.cl_size[ci] = V.cneed[t];      // hole pixels that the back end will read
             V.cl_fill[ci] = 0;
@@ -463,7 +465,7 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int TELEA_WARPS = 16;
+constexpr int TELEA_WARPS = 8;
 // Two compute tasks of one generation whose pixels are closer than this (Chebyshev) run in queue order;
 // farther apart they commute.  Inpainting a pixel reads flags / T / colours within 4 of it and writes only
 // the pixel itself -> 4.  An outer-ring distance reads the 4-neighbours and writes the pixel -> 1.
@@ -727,7 +729,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
 #endif
 }
 
-__global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
+__global__ void __launch_bounds__(TELEA_WARPS * 32, 4) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
     __shared__ MarchShared sh;
     __shared__ TapTable tp;
     if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
@@ -735,15 +737,15 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const _
     const int lane = threadIdx.x & 31;
     const int v = blockIdx.y;
     const TeleaView& V = a.v[v];
-    const int nbig = a.fs->nbig[v], ncl = nbig + a.fs->nsmall[v];
-    if (a.fs->qbump[v] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
-        if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&a.fs->overflow, a.fs->qbump[v]);
+    const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
+    if (V.fs->qbump[V.vi] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&V.fs->overflow, V.fs->qbump[V.vi]);
         return;
     }
     Marcher mc{V, a.Hs, a.Ws, lane, &sh.win[threadIdx.x >> 5], &tp, 0, 0};
     const int cap = a.tw * a.th;
     while (true) {
-        if (threadIdx.x == 0) sh.ci = atomicAdd(&a.fs->next[v], 1);
+        if (threadIdx.x == 0) sh.ci = atomicAdd(&V.fs->next[V.vi], 1);
         __syncthreads();
         const int i = sh.ci;
         if (i >= ncl) break;
@@ -751,9 +753,9 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32) telea_cluster_kernel(const _
         const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
         const int* tiles = V.tile_list + V.cl_toff[ci];
         if (threadIdx.x == 0) sh.need_left = V.cl_size[ci];
-        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.keep_x0[v], a.keep_x1[v], a.stats ? a.stats + (v * 2 + 0) * 16 : nullptr);
+        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 0) * 16 : nullptr);
         __syncthreads();
-        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, a.keep_x0[v], a.keep_x1[v], a.stats ? a.stats + (v * 2 + 1) * 16 : nullptr);
+        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 1) * 16 : nullptr);
         __syncthreads();
     }
 }

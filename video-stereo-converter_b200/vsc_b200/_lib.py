@@ -18,7 +18,8 @@ DEPTH_U8, DEPTH_U16, DEPTH_F32 = 0, 1, 2
 GPU_ERROR_EXIT_CODE = 100      # sbs_generator.py:41
 
 EXPORTS = [
-    'vsc_abi_version', 'vsc_last_error', 'vsc_default_params', 'vsc_create', 'vsc_destroy', 'vsc_device',
+    'vsc_abi_version', 'vsc_last_error', 'vsc_default_params', 'vsc_create', 'vsc_create_grouped', 'vsc_group_size',
+    'vsc_submit_group', 'vsc_submit_device_group', 'vsc_destroy', 'vsc_device',
     'vsc_num_slots', 'vsc_geometry', 'vsc_process_frame', 'vsc_host_alloc', 'vsc_host_free', 'vsc_submit',
     'vsc_wait', 'vsc_query', 'vsc_submit_device', 'vsc_sync', 'vsc_slot_stream', 'vsc_slot_elapsed_ms', 'vsc_slot_launches',
     'vsc_stage_lanczos', 'vsc_stage_depth', 'vsc_stage_warp', 'vsc_stage_bilateral', 'vsc_stage_inpaint',
@@ -67,6 +68,10 @@ def load():
     lib.vsc_default_params.argtypes = [C.POINTER(VscParams)]
     lib.vsc_default_params.restype = None
     lib.vsc_create.argtypes = [i, i, C.POINTER(vp)]
+    lib.vsc_create_grouped.argtypes = [i, i, i, C.POINTER(vp)]
+    lib.vsc_group_size.argtypes = [vp]
+    lib.vsc_submit_group.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp), i, i, i, C.POINTER(VscParams), C.POINTER(vp)]
+    lib.vsc_submit_device_group.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp), i, i, i, C.POINTER(VscParams), C.POINTER(vp)]
     lib.vsc_destroy.argtypes = [vp]
     lib.vsc_destroy.restype = None
     lib.vsc_device.argtypes = [vp]
@@ -170,12 +175,12 @@ class PinnedBuffer:
 class Context:
     """Owns a vsc_ctx (one CUDA device, n_slots frames in flight)."""
 
-    def __init__(self, device: int = 0, n_slots: int = 1):
+    def __init__(self, device: int = 0, n_slots: int = 1, group_size: int = 1):
         self._lib = load()
         h = C.c_void_p()
-        check(self._lib.vsc_create(int(device), int(n_slots), C.byref(h)))
+        check(self._lib.vsc_create_grouped(int(device), int(n_slots), int(group_size), C.byref(h)))
         self._h = h
-        self.device, self.n_slots = int(device), int(n_slots)
+        self.device, self.n_slots, self.group_size = int(device), int(n_slots), int(group_size)
 
     def close(self):
         if getattr(self, '_h', None):

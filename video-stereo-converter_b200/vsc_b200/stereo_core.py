@@ -161,13 +161,14 @@ class StereoGenerator:
     """
     _DEFAULT_PARAMS = StereoParams()
 
-    def __init__(self, device: str, n_slots: int = 1) -> None:
+    def __init__(self, device: str, n_slots: int = 1, group_size: int = 1) -> None:
         self.device = device
-        self._ctx = _lib.Context(_parse_device(device), n_slots)
+        self._ctx = _lib.Context(_parse_device(device), n_slots, group_size)
         self._lib = _lib.load()
-        self.n_slots = n_slots
-        self._pending = [None] * n_slots        # per slot: (out array, owner tuple keeping inputs alive)
-        self._pinned = [None] * n_slots         # per slot: (key, rgb PinnedBuffer, depth PinnedBuffer, out PinnedBuffer)
+        self.n_slots, self.group_size = n_slots, group_size
+        self._pending = [None] * n_slots        # per slot: number of frames in flight
+        # pinned staging per (slot, frame index within the slot's group): (key, rgb, depth, out) PinnedBuffers
+        self._pinned = [[None] * group_size for _ in range(n_slots)]
 
     # -- reference API ---------------------------------------------------------------------------
     def process_frame(self, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> np.ndarray:
@@ -181,10 +182,10 @@ class StereoGenerator:
         return out
 
     # -- asynchronous pipeline ---------------------------------------------------------------------
-    def pinned_inputs(self, slot: int, h: int, w: int, depth_dtype=np.uint8):
-        """Page-locked (rgb[h,w,3], depth[h,w]) arrays of `slot` for a loader to decode into."""
+    def pinned_inputs(self, slot: int, h: int, w: int, depth_dtype=np.uint8, index: int = 0):
+        """Page-locked (rgb[h,w,3], depth[h,w]) arrays of frame `index` of `slot` for a loader to decode into."""
         key = (int(h), int(w), np.dtype(depth_dtype).str)
-        pin = self._pinned[slot]
+        pin = self._pinned[slot][index]
         if pin is None or pin[0] != key:
             if self._pending[slot] is not None:
                 raise RuntimeError(f'slot {slot} has an uncollected frame')
@@ -193,44 +194,60 @@ class StereoGenerator:
                     b.free()
             pin = (key, _lib.PinnedBuffer((h, w, 3), np.uint8), _lib.PinnedBuffer((h, w), depth_dtype),
                    _lib.PinnedBuffer((h, 2 * w, 3), np.uint8))
-            self._pinned[slot] = pin
+            self._pinned[slot][index] = pin
         return pin[1].array, pin[2].array
 
-    def submit_pinned(self, slot: int, params: StereoParams | None = None) -> None:
-        """Enqueue H2D + kernels + D2H for the frame currently in the slot's pinned input arrays."""
+    def submit_pinned(self, slot: int, params: StereoParams | None = None, n: int = 1) -> None:
+        """Enqueue H2D + kernels + D2H for the n frames currently in the slot's pinned input arrays."""
         p = params or self._DEFAULT_PARAMS
-        pin = self._pinned[slot]
-        if pin is None:
-            raise RuntimeError('call pinned_inputs(slot, h, w, dtype) first')
+        pins = self._pinned[slot][:n]
+        if any(x is None for x in pins):
+            raise RuntimeError('call pinned_inputs(slot, h, w, dtype, index) for every frame first')
         if self._pending[slot] is not None:
             raise RuntimeError(f'slot {slot} has an uncollected frame')
-        h, w, _ = pin[0]
-        _lib.check(self._lib.vsc_submit(self._ctx.handle, slot, _lib.ptr(pin[1].array), _lib.ptr(pin[2].array),
-                                        _lib.depth_code(pin[2].array.dtype), h, w, C.byref(_lib.make_params(p)),
-                                        _lib.ptr(pin[3].array)))
-        self._pending[slot] = (h, w)
+        if len({x[0] for x in pins}) != 1:
+            raise ValueError('the frames of one submission must share size and depth dtype')
+        h, w, _ = pins[0][0]
+        vp = C.c_void_p * n
+        _lib.check(self._lib.vsc_submit_group(
+            self._ctx.handle, slot, n, vp(*[x[1].array.ctypes.data for x in pins]), vp(*[x[2].array.ctypes.data for x in pins]),
+            _lib.depth_code(pins[0][2].array.dtype), h, w, C.byref(_lib.make_params(p)), vp(*[x[3].array.ctypes.data for x in pins])))
+        self._pending[slot] = n
 
     def submit(self, slot: int, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> None:
-        """Copy the frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
-        rgb_c, depth_c, _ = self._check_inputs(rgb, depth)
-        h, w = rgb_c.shape[:2]
-        prgb, pdepth = self.pinned_inputs(slot, h, w, depth_c.dtype)
-        np.copyto(prgb, rgb_c)
-        np.copyto(pdepth, depth_c)
-        self.submit_pinned(slot, params)
+        """Copy one frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
+        self.submit_frames(slot, [(rgb, depth)], params)
 
-    def collect(self, slot: int, copy: bool = True) -> np.ndarray:
-        """Wait for the slot's frame.  copy=True returns a fresh array the caller owns (the reference
-        hands its result to another thread, sbs_generator.py:325, so it must not alias a reused
-        buffer); copy=False returns the pinned output, valid until the slot is submitted again."""
-        if self._pending[slot] is None:
+    def submit_frames(self, slot: int, frames, params: StereoParams | None = None) -> None:
+        """Same for up to `group_size` frames of identical size (they share the slot's stream and one
+        hole-filling launch)."""
+        frames = list(frames)
+        if not 1 <= len(frames) <= self.group_size:
+            raise ValueError(f'a slot takes 1..{self.group_size} frames per submission')
+        for i, (rgb, depth) in enumerate(frames):
+            rgb_c, depth_c, _ = self._check_inputs(rgb, depth)
+            h, w = rgb_c.shape[:2]
+            prgb, pdepth = self.pinned_inputs(slot, h, w, depth_c.dtype, i)
+            np.copyto(prgb, rgb_c)
+            np.copyto(pdepth, depth_c)
+        self.submit_pinned(slot, params, len(frames))
+
+    def collect(self, slot: int, copy: bool = True):
+        """Wait for the slot's submission.  Returns the SBS frame (a list of frames if more than one was
+        submitted).  copy=True returns fresh arrays the caller owns (the reference hands its result to another
+        thread, sbs_generator.py:325, so it must not alias a reused buffer); copy=False returns the pinned
+        outputs, valid until the slot is submitted again."""
+        n = self._pending[slot]
+        if n is None:
             raise RuntimeError(f'slot {slot} has no frame in flight')
         try:
             _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
         finally:
             self._pending[slot] = None
-        out = self._pinned[slot][3].array
-        return out.copy() if copy else out
+        outs = [self._pinned[slot][i][3].array for i in range(n)]
+        if copy:
+            outs = [o.copy() for o in outs]
+        return outs[0] if n == 1 else outs
 
     def submit_device(self, slot: int, d_rgb: int, d_depth: int, depth_dtype, h: int, w: int, d_out: int,
                       params: StereoParams | None = None) -> None:
@@ -239,6 +256,16 @@ class StereoGenerator:
         _lib.check(self._lib.vsc_submit_device(self._ctx.handle, slot, C.c_void_p(d_rgb), C.c_void_p(d_depth),
                                                _lib.depth_code(depth_dtype), h, w, C.byref(_lib.make_params(p)),
                                                C.c_void_p(d_out)))
+
+    def submit_device_group(self, slot: int, triples, depth_dtype, h: int, w: int, params: StereoParams | None = None) -> None:
+        """Device-resident group submission: `triples` = [(d_rgb, d_depth, d_out) raw device pointers] (<= group_size)."""
+        p = params or self._DEFAULT_PARAMS
+        triples = list(triples)
+        n = len(triples)
+        vp = C.c_void_p * n
+        _lib.check(self._lib.vsc_submit_device_group(
+            self._ctx.handle, slot, n, vp(*[t[0] for t in triples]), vp(*[t[1] for t in triples]), _lib.depth_code(depth_dtype),
+            h, w, C.byref(_lib.make_params(p)), vp(*[t[2] for t in triples])))
 
     def wait(self, slot: int) -> None:
         _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
@@ -285,19 +312,38 @@ class StereoGenerator:
 
     def process_batch(self, frames: Iterable[Tuple[np.ndarray, np.ndarray]],
                       params: StereoParams | None = None) -> List[np.ndarray]:
-        """Run an iterable of (rgb, depth) through all slots, keeping `n_slots` frames in flight."""
-        out: List[np.ndarray] = []
-        inflight: List[int] = []
-        nxt = 0
-        for rgb, depth in frames:
-            if len(inflight) == self.n_slots:
-                out.append(self.collect(inflight.pop(0)))
-            self.submit(nxt, rgb, depth, params)
-            inflight.append(nxt)
-            nxt = (nxt + 1) % self.n_slots
-        while inflight:
-            out.append(self.collect(inflight.pop(0)))
-        return out
+        """Run an iterable of (rgb, depth) through all slots, keeping `n_slots * group_size` frames in flight.
+        Results are returned in input order."""
+        frames = list(frames)
+        out: List[Optional[np.ndarray]] = [None] * len(frames)
+        g = self.group_size
+        chunks = [list(range(i, min(i + g, len(frames)))) for i in range(0, len(frames), g)]
+        inflight: List[Tuple[int, List[int]]] = []
+        free = list(range(self.n_slots))
+
+        def harvest(slot, idxs):
+            res = self.collect(slot)
+            res = res if isinstance(res, list) else [res]
+            for i, r in zip(idxs, res):
+                out[i] = r
+            free.append(slot)
+
+        for idxs in chunks:
+            # frames of one submission must share size / dtype: fall back to singles otherwise
+            keys = {(frames[i][0].shape, frames[i][1].shape, frames[i][1].dtype.str) for i in idxs}
+            parts = [idxs] if len(keys) == 1 else [[i] for i in idxs]
+            for part in parts:
+                if not free:
+                    slot = self.wait_any([s for s, _ in inflight])
+                    ids = next(x for s, x in inflight if s == slot)
+                    inflight.remove((slot, ids))
+                    harvest(slot, ids)
+                slot = free.pop(0)
+                self.submit_frames(slot, [frames[i] for i in part], params)
+                inflight.append((slot, part))
+        for slot, ids in inflight:
+            harvest(slot, ids)
+        return out  # type: ignore[return-value]
 
     def last_frame_ms(self, slot: int = 0) -> float:
         ms = C.c_float()
@@ -308,11 +354,12 @@ class StereoGenerator:
         return int(self._lib.vsc_slot_launches(self._ctx.handle, slot))
 
     def close(self) -> None:
-        for pin in self._pinned:
-            if pin is not None:
-                for b in pin[1:]:
-                    b.free()
-        self._pinned = [None] * self.n_slots
+        for row in self._pinned:
+            for pin in row:
+                if pin is not None:
+                    for b in pin[1:]:
+                        b.free()
+        self._pinned = [[None] * self.group_size for _ in range(self.n_slots)]
         self._ctx.close()
 
     # -- helpers -----------------------------------------------------------------------------------
