@@ -116,6 +116,15 @@ def test_queue_scratch_overflow_is_detected_and_rerun():
         assert all(np.array_equal(o, ref) for o in outs)
     finally:
         g.close()
+    g = StereoGenerator('cuda', n_slots=1, group_size=3)         # the whole group is re-run when one frame overflows
+    try:
+        _lib.check(lib.vsc_debug_set_telea_capacity(g._ctx.handle, 64))
+        rgb2, depth2 = make_pair(120, 200, seed=22)
+        outs = g.process_batch([(rgb, depth), (rgb2, depth2), (rgb, depth)], StereoParams(**kw))
+        assert np.array_equal(outs[0], ref) and np.array_equal(outs[2], ref)
+        assert np.array_equal(outs[1], O.process_frame(rgb2, depth2, O.Params(**kw)))
+    finally:
+        g.close()
 
 
 def test_grouped_slots_match_single_frames():
