@@ -307,7 +307,10 @@ static int set_smem_attrs() {
     CU(cudaFuncSetAttribute(depth_front_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(depth_front_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(backend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(backend_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(backend_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(backend_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(backend_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return VSC_OK;
 }
 
@@ -624,8 +627,11 @@ static int run_backend(Slot& s, const vsc_geom& g, double sharpen, const uchar4*
     a.view[0] = v0; a.view[1] = v1; a.out = d_out;
     a.H = g.height; a.W = g.width; a.Hs = g.ss_h; a.Ws = g.ss_w;
     a.crop[0] = g.left_crop; a.crop[1] = g.right_crop; a.cw = g.crop_w;
-    a.RH = (int)(((long long)BE_OY * g.ss_h + g.height - 1) / g.height) + 1;
-    a.RW = (int)(((long long)BE_OX * g.crop_w + g.width - 1) / g.width) + 1;
+    // integer super-sampling (the usual case): compile-time tile geometry
+    int K = 0;
+    for (int k = 2; k <= 4; k++) if (g.ss_h == k * g.height && g.crop_w == k * g.width) K = k;
+    a.RH = K ? BE_OY * K : (int)(((long long)BE_OY * g.ss_h + g.height - 1) / g.height) + 1;
+    a.RW = K ? BE_OX * K + 1 : (int)(((long long)BE_OX * g.crop_w + g.width - 1) / g.width) + 1;
     a.strength = (float)sharpen;
     a.do_sharpen = sharpen > 0;
     a.g5 = gauss_taps(5, 1.0);
@@ -634,7 +640,12 @@ static int run_backend(Slot& s, const vsc_geom& g, double sharpen, const uchar4*
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "super_sampling too large for the back-end tile (%zu bytes of shared memory)", smem);
     dim3 grid((g.width + BE_OX - 1) / BE_OX, (g.height + BE_OY - 1) / BE_OY, 2);
     prof_begin(s, "backend_kernel");
-    backend_kernel<<<grid, kThreads, smem, s.stream>>>(a);
+    switch (K) {
+        case 2: backend_kernel<2><<<grid, kThreads, smem, s.stream>>>(a); break;
+        case 3: backend_kernel<3><<<grid, kThreads, smem, s.stream>>>(a); break;
+        case 4: backend_kernel<4><<<grid, kThreads, smem, s.stream>>>(a); break;
+        default: backend_kernel<0><<<grid, kThreads, smem, s.stream>>>(a); break;
+    }
     KCHECK(s);
     return VSC_OK;
 }
