@@ -306,7 +306,9 @@ static int set_smem_attrs() {
     CU(cudaFuncSetAttribute(lanczos_depth_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(depth_front_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(depth_front_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -490,10 +492,11 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
     return VSC_OK;
 }
 static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint8_t* d_rgb_st, const float* d_depth_ss,
-                    uchar4* vl, uchar4* vr, uint8_t* ml, uint8_t* mr, int mode) {
+                    uchar4* vl, uchar4* vr, uint8_t* ml, uint8_t* mr, unsigned* hl, unsigned* hr, int mode) {
     WarpArgs a;
     a.rgb_st = d_rgb_st; a.depth = d_depth_ss; a.ty = s.d_ty; a.tx = s.d_tx;
     a.view[0] = vl; a.view[1] = vr; a.mask[0] = ml; a.mask[1] = mr;
+    a.holes[0] = hl; a.holes[1] = hr; a.wb = (g.ss_w + 31) / 32;
     a.fs = s.scalars.as<FrameScalars>();
     a.H = g.height; a.SW = g.stretched_w; a.Hs = g.ss_h; a.Ws = g.ss_w;
     a.upsample = g.super_sampled;
@@ -508,7 +511,11 @@ static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint
     const size_t smem = (size_t)4 * a.TS * 4 + 2 * ((size_t)a.TS * 4 + 16) + 2 * (size_t)a.rgb_stage_bytes;
     dim3 grid(nseg, g.ss_h);
     prof_begin(s, "warp_kernel");
-    warp_kernel<<<grid, kThreads, smem, s.stream>>>(a);
+    switch (mode) {
+        case 0: warp_kernel<0><<<grid, kThreads, smem, s.stream>>>(a); break;
+        case 1: warp_kernel<1><<<grid, kThreads, smem, s.stream>>>(a); break;
+        default: warp_kernel<2><<<grid, kThreads, smem, s.stream>>>(a); break;
+    }
     KCHECK(s);
     return VSC_OK;
 }
@@ -561,7 +568,7 @@ struct ViewSpec {       // one eye of one frame for the hole-filling launch
     Slot* fr;           // the frame slot that owns the scratch buffers and the frame scalars
     int b;              // 0 = left, 1 = right
     uchar4* img;
-    const uint8_t* valid;
+    const unsigned* holes;   // hole bitmap written by the warp kernel (or pack_holes_kernel)
     int k0, k1;         // columns the back end reads
 };
 // `s` is the group leader (stream, launch / profiling bookkeeping); the views may belong to several frame slots
@@ -572,6 +579,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
     memset(&a, 0, sizeof a);
     a.Hs = Hs; a.Ws = Ws; a.tw = (Ws + TG - 1) / TG; a.th = (Hs + TG - 1) / TG;
     a.nviews = nviews;
+    a.wb = (Ws + 31) / 32;
 #ifdef VSC_TELEA_STATS
     if (s.tstats.ensure(64 * 8)) return VSC_E_NOMEM;
     CU(cudaMemsetAsync(s.tstats.p, 0, 64 * 8, s.stream));
@@ -582,7 +590,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
         Slot& f = *vs[v].fr;
         const int b = vs[v].b;
         TeleaView& V = a.v[v];
-        V.img = vs[v].img; V.valid = vs[v].valid;
+        V.img = vs[v].img; V.holes = vs[v].holes;
         V.st = f.st[b].as<uint8_t>(); V.tt = f.tt[b].as<float>();
         V.tile_cnt = f.tile_u8[b].as<unsigned char>(); V.tile_need = V.tile_cnt + nt;
         int* ib = f.tile_i32[b].as<int>();
@@ -596,9 +604,9 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
         V.fs = f.scalars.as<FrameScalars>();
         V.vi = b;
         V.keep_x0 = vs[v].k0; V.keep_x1 = vs[v].k1;
-        CU(cudaMemsetAsync(f.pstate[b].p, 0xff, (size_t)Hs * Ws * 4, s.stream));   // every pixel: 'task done'
     }
-    dim3 pgrid((Ws + 31) / 32, (Hs + 31) / 32, nviews), pblock(32, 8);
+    // the prepare kernel also resets the dataflow words (pstate) within reach of a hole; the rest is never read
+    dim3 pgrid((Ws + 31) / 32, (Hs + PR_ROWS * 8 - 1) / (PR_ROWS * 8), nviews), pblock(32, 8);
     prof_begin(s, "telea_prepare_kernel");
     telea_prepare_kernel<<<pgrid, pblock, 0, s.stream>>>(a);
     KCHECK(s);
@@ -635,8 +643,9 @@ static int run_backend(Slot& s, const vsc_geom& g, double sharpen, const uchar4*
     a.strength = (float)sharpen;
     a.do_sharpen = sharpen > 0;
     a.g5 = gauss_taps(5, 1.0);
-    const size_t smem = (size_t)(a.RH + 4) * (a.RW + 4) * 4 + (size_t)3 * (a.RH + 4) * a.RW * 4 + (size_t)3 * a.RH * a.RW * 4 +
-                        (size_t)BE_OY * (BE_OX * 3 + 16);
+    // staged input + horizontally blurred planes (+ sharpened planes unless K == 3 pools from registers) + output bytes
+    const size_t smem = (size_t)(a.RH + 4) * (a.RW + 4) * 4 + (size_t)3 * (a.RH + 4) * a.RW * 4 +
+                        (K == 3 ? 0 : (size_t)3 * a.RH * a.RW * 4) + (size_t)BE_OY * (BE_OX * 3 + 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "super_sampling too large for the back-end tile (%zu bytes of shared memory)", smem);
     dim3 grid((g.width + BE_OX - 1) / BE_OX, (g.height + BE_OY - 1) / BE_OY, 2);
     prof_begin(s, "backend_kernel");
@@ -661,7 +670,7 @@ static int ensure_frame_buffers(Slot& s, const vsc_geom& g, bool smoothing) {
     for (int v = 0; v < 2; v++) {
         rc |= s.viewA[v].ensure(npx * 4);
         if (smoothing) rc |= s.viewB[v].ensure(npx * 4);
-        rc |= s.vmask[v].ensure(npx);
+        rc |= s.vmask[v].ensure((size_t)g.ss_h * ((g.ss_w + 31) / 32) * 4);     // hole bitmap, 1 bit per pixel
     }
     return rc ? VSC_E_NOMEM : VSC_OK;
 }
@@ -692,12 +701,12 @@ static int enqueue_group(vsc_ctx* ctx, Slot* fr, int n, int dtype, const vsc_geo
         if ((rc = run_lanczos_depth(s, s.l_depth, dtype, g.height, g.width, g.stretched_w, s.depth_st.as<float>()))) return rc;
         if ((rc = run_depth_front(ctx, s, g, p, s.depth_st.as<float>(), s.depth_ss.as<float>()))) return rc;
         uchar4* va[2] = {s.viewA[0].as<uchar4>(), s.viewA[1].as<uchar4>()};
-        uint8_t* vm[2] = {s.vmask[0].as<uint8_t>(), s.vmask[1].as<uint8_t>()};
-        if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 0))) return rc;
+        unsigned* vm[2] = {s.vmask[0].as<unsigned>(), s.vmask[1].as<unsigned>()};     // hole bitmaps
+        if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], nullptr, nullptr, vm[0], vm[1], 0))) return rc;
         cur[2 * i] = va[0]; cur[2 * i + 1] = va[1];
         if (smoothing) {
             // `if image_np.max() > 1.0 ... else (image_np * 255)` (stereo_core.py:404-407): conditional re-run on device
-            if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], vm[0], vm[1], 1))) return rc;
+            if ((rc = run_warp(s, g, p.max_disparity, s.rgb_st.as<uint8_t>(), s.depth_ss.as<float>(), va[0], va[1], nullptr, nullptr, vm[0], vm[1], 1))) return rc;
             uchar4* vb[2] = {s.viewB[0].as<uchar4>(), s.viewB[1].as<uchar4>()};
             if ((rc = run_bilateral(ctx, s, g.ss_h, g.ss_w, p.artifact_smoothing, va[0], va[1], vb[0], vb[1], 2))) return rc;
             cur[2 * i] = vb[0]; cur[2 * i + 1] = vb[1];
@@ -965,8 +974,8 @@ extern "C" int vsc_stage_warp(vsc_ctx* ctx, const uint8_t* rgb_st, const float* 
     if (drgb.alloc(nr) || dd.alloc(ns * 4) || v0.alloc(ns * 4) || v1.alloc(ns * 4)) return VSC_E_NOMEM;
     CU(cudaMemcpyAsync(drgb.p, rgb_st, nr, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(dd.p, depth_ss, ns * 4, cudaMemcpyHostToDevice, s.stream));
-    if ((rc = run_warp(s, g, max_disparity, (const uint8_t*)drgb.p, (const float*)dd.p, (uchar4*)v0.p, (uchar4*)v1.p, nullptr, nullptr, 0))) return rc;
-    if (scale255 && (rc = run_warp(s, g, max_disparity, (const uint8_t*)drgb.p, (const float*)dd.p, (uchar4*)v0.p, (uchar4*)v1.p, nullptr, nullptr, 2))) return rc;
+    if ((rc = run_warp(s, g, max_disparity, (const uint8_t*)drgb.p, (const float*)dd.p, (uchar4*)v0.p, (uchar4*)v1.p, nullptr, nullptr, nullptr, nullptr, 0))) return rc;
+    if (scale255 && (rc = run_warp(s, g, max_disparity, (const uint8_t*)drgb.p, (const float*)dd.p, (uchar4*)v0.p, (uchar4*)v1.p, nullptr, nullptr, nullptr, nullptr, 2))) return rc;
     std::vector<uchar4> h0(ns), h1(ns);
     FrameScalars fs;
     CU(cudaMemcpyAsync(h0.data(), v0.p, ns * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -1015,11 +1024,14 @@ extern "C" int vsc_stage_inpaint(vsc_ctx* ctx, uint8_t* img, const uint8_t* vali
     Tmp dimg, dval;
     int rc = upload_view(s, img, valid, n, dimg);
     if (rc) return rc;
-    if (dval.alloc(n)) return VSC_E_NOMEM;
+    Tmp dbits;
+    const int wb = (W + 31) / 32;
+    if (dval.alloc(n) || dbits.alloc((size_t)H * wb * 4)) return VSC_E_NOMEM;
     CU(cudaMemcpyAsync(dval.p, valid, n, cudaMemcpyHostToDevice, s.stream));
+    pack_holes_kernel<<<ctx->sm_count * 8, kThreads, 0, s.stream>>>((const uint8_t*)dval.p, H, W, wb, (unsigned*)dbits.p);
     for (int attempt = 0; attempt < 4; attempt++) {
         frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
-        ViewSpec one{&s, 0, (uchar4*)dimg.p, (const uint8_t*)dval.p, keep_x0, keep_x0 + keep_w};
+        ViewSpec one{&s, 0, (uchar4*)dimg.p, (const unsigned*)dbits.p, keep_x0, keep_x0 + keep_w};
         if ((rc = run_telea(ctx, s, H, W, &one, 1))) return rc;
         CU(cudaMemcpyAsync(s.h_scalars, s.scalars.p, sizeof(FrameScalars), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
@@ -1113,7 +1125,7 @@ extern "C" int vsc_debug_telea_state(vsc_ctx* ctx, int view, float* tt, uint8_t*
 }
 
 // debug: copy an intermediate buffer of slot 0 (after a completed frame) to the host.
-// which: 0 rgb_st, 1 depth_st (normalised), 2 depth_ss, 3/4 viewA L/R, 5/6 viewB L/R, 7/8 vmask L/R
+// which: 0 rgb_st, 1 depth_st (normalised), 2 depth_ss, 3/4 viewA L/R, 5/6 viewB L/R, 7/8 hole bitmaps L/R
 extern "C" int vsc_debug_fetch(vsc_ctx* ctx, int which, void* dst, size_t bytes) {
     if (!ctx || !dst) return fail(VSC_E_INVALID, "null argument");
     Slot& s = ctx->slots[0];

@@ -33,7 +33,7 @@ constexpr int TG = 8;   // tile edge for clustering
 
 struct TeleaView {
     uchar4* img;            // [Hs][Ws] in/out (alpha = validity from the warp)
-    const uint8_t* valid;   // [Hs][Ws] 1 = valid (compact copy of alpha)
+    const unsigned* holes;  // [Hs][wb] hole bitmap (bit i of word j <-> column 32 j + i; 1 = alpha 0)
     uint8_t* st;            // [Hs][Ws]
     float* tt;              // [Hs][Ws]
     // tile grid
@@ -60,91 +60,130 @@ constexpr int TELEA_MAX_VIEWS = 8;   // a march launch covers up to 4 frames x 2
 struct TeleaArgs {
     TeleaView v[TELEA_MAX_VIEWS];
     int Hs, Ws, tw, th;
+    int wb;                      // words per row of the hole bitmaps
     int nviews;
     unsigned long long* stats;   // optional [2 views][2 passes][16] counters (VSC_TELEA_STATS builds)
 };
 
 // ---- 1. morphology ----------------------------------------------------------------------------
-// One CTA = 32x32 pixels.  The hole mask of the tile (+5 apron) is packed into one 64-bit word per row, so
-// the 3x3 dilation, the 4-neighbour band, and the 7x7 / 9x9 neighbourhood tests are a few shifts and ORs
-// per row instead of an 81-tap loop per pixel.
+// Input: the hole bitmap the warp kernel wrote (1 bit per pixel, 32 columns per word).  One WARP owns a tile
+// of 32 columns x 16 rows: lane r holds image row Y0 - 5 + r of the tile (+5 apron) as one 64-bit word, so the
+// 3x3 dilation, the 4-neighbour band and the 7x7 / 9x9 neighbourhood tests are a few shifts, ORs and
+// shuffles per row.  No shared memory, no CTA barrier; tiles without a hole nearby (the common case) only
+// clear their state bytes.
 __device__ __forceinline__ unsigned long long hdil(unsigned long long m, int r) {   // horizontal dilation by r
     unsigned long long o = m;
     for (int d = 1; d <= r; d++) o |= (m << d) | (m >> d);
     return o;
 }
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int d) {
+    return ((unsigned long long)__shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), d) << 32) | __shfl_up_sync(0xffffffffu, (unsigned)v, d);
+}
+__device__ __forceinline__ unsigned long long shfl_down64(unsigned long long v, int d) {
+    return ((unsigned long long)__shfl_down_sync(0xffffffffu, (unsigned)(v >> 32), d) << 32) | __shfl_down_sync(0xffffffffu, (unsigned)v, d);
+}
+__device__ __forceinline__ unsigned vdil1(unsigned v) {    // OR with the rows above and below (lane -1 / +1)
+    return v | __shfl_up_sync(0xffffffffu, v, 1) | __shfl_down_sync(0xffffffffu, v, 1);
+}
+__device__ __forceinline__ unsigned vdil2(unsigned v) {    // OR with the rows two above and two below
+    return v | __shfl_up_sync(0xffffffffu, v, 2) | __shfl_down_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ unsigned spread4(unsigned nib) { return (nib * 0x00204081u) & 0x01010101u; }   // bit i -> byte i
+
+constexpr int PR_ROWS = 16;     // output rows per warp (two 8x8 tile rows); window rows = PR_ROWS + 10 <= 32 lanes
 __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_constant__ TeleaArgs a) {
-    __shared__ unsigned long long h0[42], M[42], B[42], R3[42], N4[42];
     const int v = blockIdx.z;
     const TeleaView& V = a.v[v];
-    const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
-    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, wid = threadIdx.y;
-    // bit i of a row word <-> image column X0 - 5 + i; row r <-> image row Y0 - 5 + r
-    for (int r = wid; r < 42; r += 8) {
-        const int y = Y0 - 5 + r;
-        const bool yin = y >= 0 && y < a.Hs;
-        const int x0 = X0 - 5 + lane, x1 = X0 + 27 + lane;
-        const bool b0 = yin && x0 >= 0 && x0 < a.Ws && V.valid[(size_t)y * a.Ws + x0] == 0;
-        const bool b1 = yin && lane < 10 && x1 < a.Ws && V.valid[(size_t)y * a.Ws + x1] == 0;
-        const unsigned w0 = __ballot_sync(0xffffffffu, b0), w1 = __ballot_sync(0xffffffffu, b1);
-        if (lane == 0) h0[r] = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+    const int lane = threadIdx.x;
+    const int X0 = blockIdx.x * 32, Y0 = (blockIdx.y * (kThreads / 32) + threadIdx.y) * PR_ROWS;
+    if (Y0 >= a.Hs) return;
+    // lane <-> image row Y0 - 5 + lane; bit i of a row word <-> image column X0 - 5 + i (42 bits used)
+    const int y = Y0 - 5 + lane;
+    const bool yin = lane < PR_ROWS + 10 && y >= 0 && y < a.Hs;
+    unsigned long long h = 0;
+    if (yin) {
+        const unsigned* row = V.holes + (size_t)y * a.wb;
+        const int j = blockIdx.x;
+        const unsigned wm = j > 0 ? row[j - 1] : 0u, w0 = row[j], wp = j + 1 < a.wb ? row[j + 1] : 0u;
+        h = ((unsigned long long)(wm >> 27) | ((unsigned long long)w0 << 5) | ((unsigned long long)wp << 37)) & ((1ull << 42) - 1ull);
     }
-    // columns / rows of the tile window that lie inside the image
-    const int clo = max(0, 5 - X0), chi = min(42, a.Ws - (X0 - 5));      // bits [clo, chi) are image columns
-    const unsigned long long cm = ((1ull << chi) - 1ull) & ~((1ull << clo) - 1ull);
-    __syncthreads();
-    if (tid < 42) {
-        const int r = tid, y = Y0 - 5 + r;
-        unsigned long long m = 0;
-        if (r >= 1 && r <= 40 && y >= 0 && y < a.Hs) m = (hdil(h0[r - 1], 1) | hdil(h0[r], 1) | hdil(h0[r + 1], 1)) & cm;
-        M[r] = m;
-    }
-    __syncthreads();
-    if (tid < 42) {
-        const int r = tid, y = Y0 - 5 + r;
-        unsigned long long band = 0, n3 = 0, n4 = 0;
-        if (r >= 5 && r < 37 && y < a.Hs) {       // only the 32 tile rows are consumed below
-            const unsigned long long m = M[r];
-            band = ~m & (M[r - 1] | M[r + 1] | (m << 1) | (m >> 1)) & cm;
-            for (int d = -4; d <= 4; d++) {
-                n4 |= hdil(M[r + d], 4);
-                if (d >= -3 && d <= 3) n3 |= hdil(M[r + d], 3);
-            }
+    const bool orow = lane >= 5 && lane < 5 + PR_ROWS && y < a.Hs;     // this lane's row is an output row
+    unsigned m32 = 0, band32 = 0, ring32 = 0, n4 = 0;
+    const bool any_hole = __any_sync(0xffffffffu, h != 0ull);
+    if (any_hole) {
+        // columns of the window that lie inside the image
+        const int clo = max(0, 5 - X0), chi = min(42, a.Ws - (X0 - 5));
+        const unsigned long long cm = ((1ull << chi) - 1ull) & ~((1ull << clo) - 1ull);
+        const unsigned long long hd = hdil(h, 1);
+        unsigned long long M = (shfl_up64(hd, 1) | hd | shfl_down64(hd, 1)) & cm;      // dilate3x3(hole)
+        if (!(yin && lane >= 1 && lane <= PR_ROWS + 8)) M = 0;
+        const unsigned long long band = ~M & (shfl_up64(M, 1) | shfl_down64(M, 1) | (M << 1) | (M >> 1)) & cm;
+        const unsigned long long A3 = hdil(M, 3), A4 = A3 | (M << 4) | (M >> 4);
+        const unsigned n3 = vdil2(vdil1((unsigned)(A3 >> 5)));              // 7x7 neighbourhood of M
+        const unsigned n4v = vdil1(vdil2(vdil1((unsigned)(A4 >> 5))));      // 9x9 neighbourhood of M
+        if (orow) {
+            m32 = (unsigned)(M >> 5); band32 = (unsigned)(band >> 5);
+            ring32 = n3 & ~m32 & ~band32 & (unsigned)(cm >> 5);
+            n4 = n4v;
         }
-        B[r] = band; R3[r] = n3; N4[r] = n4;
     }
-    __syncthreads();
+    // ---- state bytes (and initial T / dataflow word near M): 4 rows x 8 lanes x 4 columns per step -------
+    const bool vec = (a.Ws & 3) == 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int ly = wid + 8 * j, lx = lane;
-        const int y = Y0 + ly, x = X0 + lx;
-        if (y >= a.Hs || x >= a.Ws) continue;
-        const int r = ly + 5, b = lx + 5;
-        const unsigned m = (unsigned)(M[r] >> b) & 1u, band = (unsigned)(B[r] >> b) & 1u;
-        const unsigned ring = ((unsigned)(R3[r] >> b) & 1u) & ~m & ~band;
-        const size_t p = (size_t)y * a.Ws + x;
-        V.st[p] = (unsigned char)((m ? F_INSIDE : 0) | (ring ? O_INSIDE : 0) | (band ? ST_BAND0 : 0));
-        if ((N4[r] >> b) & 1ull) V.tt[p] = band ? 0.f : 1.0e6f;
-    }
-    if (tid < 16) {
-        const int t4y = tid >> 2, t4x = tid & 3;
-        const int ty = blockIdx.y * 4 + t4y, tx = blockIdx.x * 4 + t4x;
-        if (ty < a.th && tx < a.tw) {
-            const int klo = min(8, max(0, V.keep_x0 - (X0 + 8 * t4x))), khi = max(0, min(8, V.keep_x1 - (X0 + 8 * t4x)));
-            const unsigned long long keep = khi > klo ? (((1ull << khi) - 1ull) & ~((1ull << klo) - 1ull)) : 0ull;
-            int cnt = 0, need = 0;     // need = number of M pixels inside the kept window
-            for (int i = 0; i < 8; i++) {
-                const int r = 5 + 8 * t4y + i, sh = 5 + 8 * t4x;
-                const unsigned long long m = (M[r] >> sh) & 0xffull, bd = (B[r] >> sh) & 0xffull, rg = (R3[r] >> sh) & 0xffull;
-                // rows / columns outside the image carry no M, band or ring bits: M is masked, band is masked with cm,
-                // and the ring excludes nothing there but R3 rows beyond the image are zero (r < 37 && y < Hs above)
-                const unsigned long long inimg = (cm >> sh) & 0xffull;
-                cnt += __popcll((m | bd | (rg & ~m & ~bd)) & inimg);
-                need += __popcll(m & keep);
-            }
-            V.tile_cnt[ty * a.tw + tx] = (unsigned char)cnt;
-            V.tile_need[ty * a.tw + tx] = (unsigned char)need;
+    for (int it = 0; it < PR_ROWS / 4; it++) {
+        const int rr = it * 4 + (lane >> 3), srcl = rr + 5, c0 = (lane & 7) * 4;
+        const unsigned mm = (__shfl_sync(0xffffffffu, m32, srcl) >> c0) & 0xfu;
+        const unsigned bb = (__shfl_sync(0xffffffffu, band32, srcl) >> c0) & 0xfu;
+        const unsigned rg = (__shfl_sync(0xffffffffu, ring32, srcl) >> c0) & 0xfu;
+        const unsigned nn = (__shfl_sync(0xffffffffu, n4, srcl) >> c0) & 0xfu;
+        const int yy = Y0 + rr, xx = X0 + c0;
+        if (yy >= a.Hs || xx >= a.Ws) continue;
+        const unsigned stw = spread4(mm) * F_INSIDE | spread4(rg) * O_INSIDE | spread4(bb) * ST_BAND0;
+        const size_t p = (size_t)yy * a.Ws + xx;
+        if (vec) *reinterpret_cast<unsigned*>(V.st + p) = stw;         // Ws % 4 == 0: xx + 3 < Ws and p % 4 == 0
+        else for (int k = 0; k < 4 && xx + k < a.Ws; k++) V.st[p + k] = (unsigned char)(stw >> (8 * k));
+        if (nn) {
+            for (int k = 0; k < 4 && xx + k < a.Ws; k++)
+                if ((nn >> k) & 1u) { V.tt[p + k] = ((bb >> k) & 1u) ? 0.f : 1.0e6f; V.pstate[p + k] = 0xffffffffu; }
         }
+    }
+    // ---- 8x8 tile occupancy: lanes 5..12 and 13..20 each hold the rows of one tile row ------------------
+    if (lane >= 5 && lane < 5 + PR_ROWS) {
+        const int klo = min(32, max(0, V.keep_x0 - X0)), khi = max(0, min(32, V.keep_x1 - X0));
+        const unsigned keep = khi > klo ? ((khi == 32 ? 0xffffffffu : ((1u << khi) - 1u)) & ~((1u << klo) - 1u)) : 0u;
+        const unsigned occ = m32 | band32 | ring32, need = m32 & keep;
+        unsigned pc = 0, pn = 0;       // four per-tile counts packed into bytes (each <= 8 per row, <= 64 per tile)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            pc |= (unsigned)__popc(occ & (0xffu << (8 * t))) << (8 * t);
+            pn |= (unsigned)__popc(need & (0xffu << (8 * t))) << (8 * t);
+        }
+        const int half = (lane - 5) >> 3;
+        const unsigned gm = half ? 0x001fe000u : 0x00001fe0u;
+        pc = __reduce_add_sync(gm, pc);
+        pn = __reduce_add_sync(gm, pn);
+        if (((lane - 5) & 7) == 0) {
+            const int ty = Y0 / TG + half;
+            if (ty < a.th)
+                for (int t = 0; t < 4; t++) {
+                    const int tx = X0 / TG + t;
+                    if (tx < a.tw) {
+                        V.tile_cnt[ty * a.tw + tx] = (unsigned char)(pc >> (8 * t));
+                        V.tile_need[ty * a.tw + tx] = (unsigned char)(pn >> (8 * t));
+                    }
+                }
+        }
+    }
+}
+
+// hole bitmap from a validity byte map (stage API / tests; the pipeline's warp kernel writes the bitmap itself)
+__global__ void pack_holes_kernel(const uint8_t* __restrict__ valid, int Hs, int Ws, int wb, unsigned* __restrict__ holes) {
+    const int lane = threadIdx.x & 31;
+    const size_t nw = (size_t)Hs * wb;
+    for (size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; w < nw; w += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const int y = (int)(w / wb), x = (int)(w - (size_t)y * wb) * 32 + lane;
+        const unsigned bits = __ballot_sync(0xffffffffu, x < Ws && valid[(size_t)y * Ws + x] == 0);
+        if (lane == 0) holes[w] = bits;
     }
 }
 
