@@ -8,7 +8,9 @@ A "step" is one pass of the hot path over one batch of `--batch` synthetic 1080p
 (config "1080p 300-frame synthetic clip, default config.json stereo params", BASELINE.json
 configs[1]); frames are independent, so with N GPUs every rank processes its own batch (frame-range
 sharding, no collective; "scaling": "weak") and the reported value is total frames / max-over-ranks
-device time.
+device time.  The K timed steps are K consecutive batches of ONE continuous clip: they overlap in the
+slot pipeline the way consecutive seconds of a video do, and the timed region is bracketed by a
+barrier + full drain + synchronize on both sides (pipeline fill and drain are inside it).
 
   value  frames/s with the inputs already resident in HBM (vsc_submit_device), timed with CUDA
          events across all slot streams (vsc_timer_begin/end)
@@ -119,41 +121,51 @@ def run_ours(args, rank, world, local_rank):
     d_out = [[torch.empty((H, 2 * W, 3), dtype=torch.uint8, device='cuda') for _ in range(group)] for _ in range(slots)]
     torch.cuda.synchronize()
 
-    def device_step(step):
+    # The clip is one continuous stream of frames: step k is frames [k*batch, (k+1)*batch) and consecutive steps
+    # overlap in the slot pipeline exactly as consecutive seconds of a video do.  The timed region is bracketed by
+    # a full drain + synchronize on both sides (timed()), never between steps.
+    class Pipe:
+        def __init__(self):
+            self.free, self.busy, self.last = list(range(slots)), [], None
+
+    def device_step(step, pipe):
         """one batch, inputs resident in HBM; a finished slot is reused at once (no head-of-line blocking);
         every submission carries `group` frames that share the slot's stream and one hole-filling launch"""
-        free, busy = list(range(slots)), []
         for i0 in range(0, batch, group):
-            if not free:
-                s = gen.wait_any(busy)
+            if not pipe.free:
+                s = gen.wait_any(pipe.busy)
                 gen.wait(s)
-                busy.remove(s)
-                free.append(s)
-            s = free.pop(0)
+                pipe.busy.remove(s)
+                pipe.free.append(s)
+            s = pipe.free.pop(0)
             tri = []
             for k in range(min(group, batch - i0)):
                 f = (step * batch + i0 + k) % n_distinct
                 tri.append((d_rgb[f].data_ptr(), d_dep[f].data_ptr(), d_out[s][k].data_ptr()))
             gen.submit_device_group(s, tri, DEPTH_DTYPE, H, W, params)
-            busy.append(s)
-        for s in busy:
+            pipe.busy.append(s)
+
+    def device_drain(pipe):
+        for s in pipe.busy:
             gen.wait(s)
+        pipe.free += pipe.busy
+        pipe.busy = []
 
     from concurrent.futures import ThreadPoolExecutor
     loaders = ThreadPoolExecutor(max_workers=max(1, group))
     for s_ in range(slots):          # allocate the pinned staging buffers outside the timed region
         for k_ in range(group):
             gen.pinned_inputs(s_, H, W, DEPTH_DTYPE, k_)
+    e2e_reads = []
 
-    def e2e_step(step):
-        free, busy, last = list(range(slots)), [], None
+    def e2e_step(step, pipe):
         for i0 in range(0, batch, group):
-            if not free:
-                s = gen.wait_any(busy)
-                last = gen.collect(s, copy=False)
-                busy.remove(s)
-                free.append(s)
-            s = free.pop(0)
+            if not pipe.free:
+                s = gen.wait_any(pipe.busy)
+                pipe.last = gen.collect(s, copy=False)
+                pipe.busy.remove(s)
+                pipe.free.append(s)
+            s = pipe.free.pop(0)
             n = min(group, batch - i0)
 
             def load(k, s=s, i0=i0):
@@ -164,23 +176,32 @@ def run_ours(args, rank, world, local_rank):
                 np.copyto(pdep, frames[f][1])
             list(loaders.map(load, range(n)))
             gen.submit_pinned(s, params, n)
-            busy.append(s)
-        for s in busy:
-            last = gen.collect(s, copy=False)
-        last = last[-1] if isinstance(last, list) else last
-        return int(last[0, 0, 0])      # device->host read of the step's result
+            pipe.busy.append(s)
+        if pipe.last is not None:        # host read of the newest finished SBS frame (pinned, already transferred)
+            last = pipe.last[-1] if isinstance(pipe.last, list) else pipe.last
+            e2e_reads.append(int(last[0, 0, 0]))
+
+    def e2e_drain(pipe):
+        for s in pipe.busy:
+            pipe.last = gen.collect(s, copy=False)
+        pipe.free += pipe.busy
+        pipe.busy = []
+        last = pipe.last[-1] if isinstance(pipe.last, list) else pipe.last
+        e2e_reads.append(int(last[0, 0, 0]))
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, drain, steps):
+        pipe = Pipe()
         barrier()
         gen.timer_begin()
         t0 = time.perf_counter()
         for k in range(steps):
-            fn(k)
+            fn(k, pipe)
+        drain(pipe)
         ms = gen.timer_end()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
@@ -190,14 +211,18 @@ def run_ours(args, rank, world, local_rank):
             ms, wall = float(t[0]), float(t[1])
         return ms, wall
 
+    wp = Pipe()
     for k in range(args.warmup):
-        device_step(k)
+        device_step(k, wp)
+    device_drain(wp)
     launches_per_frame = gen.last_frame_launches(0) / group
     with ClockSampler(local_rank) as clk:
-        ms_dev, wall_dev = timed(device_step, args.steps)
+        ms_dev, wall_dev = timed(device_step, device_drain, args.steps)
+    wp = Pipe()
     for k in range(max(1, args.warmup // 2)):
-        e2e_step(k)
-    ms_e2e, wall_e2e = timed(e2e_step, args.steps)
+        e2e_step(k, wp)
+    e2e_drain(wp)
+    ms_e2e, wall_e2e = timed(e2e_step, e2e_drain, args.steps)
 
     # per-kernel times for the roofline (separate, untimed pass with event pairs around every launch)
     kt = {}          # kernel name -> list over profiled frames of its summed device ms in that frame
@@ -324,7 +349,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=96, help='frames per step per GPU')
+    ap.add_argument('--batch', type=int, default=240, help='frames per step per GPU')
     ap.add_argument('--slots', type=int, default=30, help='slots (CUDA streams) per GPU')
     ap.add_argument('--group', type=int, default=4, help='frames per slot submission (share a stream and one hole-filling launch)')
     ap.add_argument('--cpu-frames', type=int, default=2)

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -623,7 +624,9 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
     prof_begin(s, "telea_cluster_fill_kernel");
     telea_cluster_fill_kernel<<<tgrid, kThreads, 0, s.stream>>>(a);  KCHECK(s);
 #ifndef VSC_EXPERIMENT_NO_MARCH
-    dim3 cgrid(ctx->sm_count / 2, nviews);   // persistent CTAs pulling clusters from a queue (big clusters first)
+    // persistent CTAs pulling clusters from a per-view queue (big clusters first); view-major launch order, so the
+    // first CTAs to start take each view's biggest cluster
+    dim3 cgrid(nviews, ctx->sm_count / 2);
     prof_begin(s, "telea_cluster_kernel");
     telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
     KCHECK(s);

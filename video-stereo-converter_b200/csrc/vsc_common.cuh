@@ -87,9 +87,12 @@ __device__ __forceinline__ void cta_copy_s2g(uint8_t* __restrict__ g, const uint
 // Same specification as the oracle's orc_powf: only IEEE-754 double +,*,/,fma and exact
 // frexp/ldexp/rint, so CPU and GPU agree bit for bit; the result is the double value rounded to
 // float, i.e. correctly rounded except for ~1e-4 of inputs.
+// x is a normal positive double here (a float in [0.001, 1]); frexp / ldexp are exact, so doing them on the
+// exponent field directly gives the same bits as the library calls without their special-case handling
 __device__ __forceinline__ double det_log2(double x) {
-    int e;
-    double m = frexp(x, &e);
+    const int hi = __double2hiint(x);
+    int e = ((hi >> 20) & 0x7ff) - 1022;
+    double m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));    // frexp: m in [0.5, 1)
     if (m < 0.70710678118654752440) { m = __dmul_rn(m, 2.0); e -= 1; }
     const double s = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
     const double z = __dmul_rn(s, s);
@@ -127,7 +130,9 @@ __device__ __forceinline__ double det_exp2(double t) {
     p = fma(p, f, 0.5);
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
-    return ldexp(p, (int)n);
+    const int k = (int)n;
+    if (k < -1000 || k > 1000) return ldexp(p, k);      // would leave the normal range: let the library round
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));          // p in (0.5, 2): exact scaling
 }
 __device__ __forceinline__ float det_powf(float x, float g) {
     if (g == 2.0f) return __fmul_rn(x, x);

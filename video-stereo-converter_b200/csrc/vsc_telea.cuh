@@ -495,38 +495,41 @@ __device__ void block_sort(unsigned long long* key, unsigned* idx, int n) {
     }
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.cta.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-    asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-constexpr int TELEA_WARPS = 8;
+#ifndef VSC_TELEA_WARPS
+#define VSC_TELEA_WARPS 8
+#endif
+constexpr int TELEA_WARPS = VSC_TELEA_WARPS;
 // Two compute tasks of one generation whose pixels are closer than this (Chebyshev) run in queue order;
 // farther apart they commute.  Inpainting a pixel reads flags / T / colours within 4 of it and writes only
 // the pixel itself -> 4.  An outer-ring distance reads the 4-neighbours and writes the pixel -> 1.
 constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
 
+constexpr int TELEA_RING = 128;       // completion ring entries (>= tasks in flight, see march)
+constexpr int TELEA_MAXDEP = 32;      // compact dependency list per warp (one entry per lane); more (rare): per-lane polling
 struct MarchShared {
     int npool, npool2, ncur, ntask, next_t, done_t, gbase, scan_total, need_left;
     unsigned tmin;
+    unsigned tbase;                    // CTA-monotonic index of the current generation's first task
     int ci;
     int wsum[TELEA_WARPS];
+    unsigned ring[TELEA_RING];         // ring[J % RING] = J + 1 once task J has finished (monotonic per entry)
+    unsigned wdep[TELEA_WARPS][TELEA_MAXDEP];
     WarpWin win[TELEA_WARPS];
 #ifdef VSC_TELEA_STATS
     unsigned long long c_wait, c_pop, c_sort, c_part, c_total, n_pops, n_pix, n_gen, n_polls, c_load, c_inp, c_rel, c_min4;
 #endif
 };
 
-// pstate word per pixel: (order key << 2) | kind | done   kind: bit1 (1 = compute task, 0 = queue pop)
-//   pop  of the current generation : (G << 2) | 1              G = global pop index (rank in sorted order)
-//   task pending                   : (K << 2) | 2              K = G*4 + q  (owner pop, neighbour index)
-//   task done / never touched      : (K << 2) | 3   /  0xffffffff
+// pstate word per pixel: (index << 2) | kind
+//   pop  of the current generation : (G << 2) | 1      G = global pop index (rank in sorted order)
+//   compute task                   : (J << 2) | 2      J = CTA-monotonic task index = order in which a sequential run
+//                                                      performs the tasks (also the FIFO tie-break of the queue)
+//   never touched                  : 0xffffffff
+// Whether task J has finished is NOT recorded here but in the CTA's shared-memory completion ring (MarchShared::ring):
+// a waiting warp polls shared memory, not global memory.
 __device__ __forceinline__ bool ps_is_pop(unsigned v) { return (v & 3u) == 1u; }
-__device__ __forceinline__ bool ps_pending_before(unsigned v, unsigned K) { return (v & 3u) == 2u && (v >> 2) < K; }
+__device__ __forceinline__ bool ps_is_task(unsigned v) { return (v & 3u) == 2u; }
+
 
 // One fast-marching pass over one cluster, executed by a whole CTA.
 //  * the queue is processed in generations (see file header); each generation is sorted CTA-wide.
@@ -535,9 +538,11 @@ __device__ __forceinline__ bool ps_pending_before(unsigned v, unsigned K) { retu
 //    tasks of a generation, ordered by (owner rank, neighbour index) = the order in which a sequential run
 //    performs them, is built up front in parallel.
 //  * the tasks then run as a dataflow: warps claim tasks in order and a task starts once every earlier task
-//    within TELEA_DC_* pixels has finished (pstate).  Tasks farther apart commute, so the result is
-//    identical to the sequential order.
-//  * the FIFO tie-break of the reference's queue is the task key K, i.e. the sequential push order.
+//    of its generation within TELEA_DC_* pixels has finished.  Tasks farther apart commute, so the result is
+//    identical to the sequential order.  The dependencies of a task are read once from pstate (which pixel
+//    belongs to which task), compacted into a short per-warp list, and then polled in the shared-memory
+//    completion ring - a handful of instructions per poll instead of a sweep over global memory.
+//  * the FIFO tie-break of the reference's queue is the task index J, i.e. the sequential push order.
 template <bool OUTER>
 __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw,
                       int keep_x0, int keep_x1, unsigned long long* stats) {
@@ -668,17 +673,14 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             if (e < ncur && own) {
                 const unsigned p = cur_i[e];
                 const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
-                const unsigned G = (unsigned)(gbase + e);
                 int j = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (!(own & (1u << q))) continue;
                     const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
                     const unsigned pn = (unsigned)y * (unsigned)Ws + (unsigned)x;
-                    const unsigned K = G * 4u + (unsigned)q;
-                    next_i[carry + off + j] = pn;
-                    next_k[carry + off + j] = (unsigned long long)K;      // T is filled in when the task runs
-                    V.pstate[pn] = (K << 2) | 2u;
+                    next_i[carry + off + j] = pn;         // key (T, J) is filled in when the task runs
+                    V.pstate[pn] = ((sh.tbase + (unsigned)(off + j)) << 2) | 2u;
                     j++;
                 }
             }
@@ -695,34 +697,61 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             j = __shfl_sync(0xffffffffu, j, 0);
             if (j >= ntask) break;
             const unsigned pn = next_i[carry + j];
-            const unsigned K = (unsigned)next_k[carry + j];
+            const unsigned tbase = sh.tbase, J = tbase + (unsigned)j;
             const int y = (int)(pn / (unsigned)Ws), x = (int)(pn - (unsigned)y * (unsigned)Ws);
             STAT_MARK();
-            {   // wait for every earlier task within TELEA_DC
+            {   // wait for every earlier task of this generation within TELEA_DC
                 constexpr int DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
                 constexpr int D = 2 * DC + 1, NIT = (D * D + 31) / 32;
-                const unsigned* addr[NIT];
-                unsigned pmask = 0;
+                unsigned* wd = sh.wdep[wid];
+                unsigned depr[NIT];
+                int nd = 0;
 #pragma unroll
                 for (int r = 0; r < NIT; r++) {
                     const int idx = lane + 32 * r;
                     const int yy = y + idx / D - DC, xx = x + idx % D - DC;
-                    addr[r] = &V.pstate[(size_t)min(max(yy, 0), Hs - 1) * Ws + min(max(xx, 0), Ws - 1)];
-                    if (idx < D * D && mc.inb(yy, xx) && ps_pending_before(ld_acquire(addr[r]), K)) pmask |= 1u << r;
-                }
-                STAT_INC(n_polls, 1);
-                while (__any_sync(0xffffffffu, pmask != 0)) {
-                    // Only the oldest unfinished tasks are on the critical path: poll them eagerly; the further a
-                    // claimed task is behind the completion front, the longer it sleeps (waiting warps must not
-                    // steal issue slots from the working ones).
-                    const int behind = j - *(volatile int*)&sh.done_t;
-                    __nanosleep(behind <= 2 ? 40 : min(behind * 150, 3000));
-#pragma unroll
-                    for (int r = 0; r < NIT; r++)
-                        if ((pmask >> r) & 1u) { if (!ps_pending_before(ld_acquire(addr[r]), K)) pmask &= ~(1u << r); }
-                    STAT_INC(n_polls, 1);
+                    unsigned dep = 0xffffffffu;
+                    if (idx < D * D && mc.inb(yy, xx)) {
+                        const unsigned v = V.pstate[(size_t)yy * Ws + xx];      // stable during the dataflow
+                        if (ps_is_task(v) && (v >> 2) >= tbase && (v >> 2) < J) dep = v >> 2;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, dep != 0xffffffffu);
+                    const int pos = nd + __popc(bal & ((1u << lane) - 1u));
+                    if (dep != 0xffffffffu && pos < TELEA_MAXDEP) wd[pos] = dep;
+                    nd += __popc(bal);
+                    depr[r] = dep;
                 }
                 __syncwarp();
+                STAT_INC(n_polls, 1);
+                if (nd > 0 && nd <= TELEA_MAXDEP) {
+                    const unsigned mine = lane < nd ? wd[lane] : 0xffffffffu;
+                    const volatile unsigned* slot = &sh.ring[mine & (TELEA_RING - 1)];
+                    bool pend = lane < nd;
+                    while (true) {
+                        if (pend) pend = *slot < mine + 1u;
+                        if (!__any_sync(0xffffffffu, pend)) break;
+                        // Only the oldest unfinished tasks are on the critical path: poll them eagerly; the further a
+                        // claimed task is behind the completion front, the longer it sleeps (waiting warps must not
+                        // steal issue slots from the working ones).
+                        const int behind = j - *(volatile int*)&sh.done_t;
+                        __nanosleep(behind <= 2 ? 40 : min(behind * 200, 4000));
+                        STAT_INC(n_polls, 1);
+                    }
+                    __threadfence_block();
+                } else if (nd > 0) {       // more dependencies than the list holds: every lane polls its own
+                    while (true) {
+                        bool pend = false;
+#pragma unroll
+                        for (int r = 0; r < NIT; r++)
+                            if (depr[r] != 0xffffffffu) {
+                                if (*(volatile unsigned*)&sh.ring[depr[r] & (TELEA_RING - 1)] >= depr[r] + 1u) depr[r] = 0xffffffffu;
+                                else pend = true;
+                            }
+                        if (!__any_sync(0xffffffffu, pend)) break;
+                        __nanosleep(100);
+                    }
+                    __threadfence_block();
+                }
             }
             STAT_ADD(c_wait);
             STAT_MARK();
@@ -737,16 +766,29 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             if (lane == 0) {
                 const unsigned char s = mc.S(y, x);
                 mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
-                next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)K;
+                next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)J;
                 if (!OUTER && x >= keep_x0 && x < keep_x1) atomicSub(&sh.need_left, 1);
             }
             __syncwarp();
-            { STAT_T0(); if (lane == 0) { st_release(&V.pstate[pn], (K << 2) | 3u); atomicAdd(&sh.done_t, 1); } __syncwarp(); STAT_T1(c_rel); }
+            {   // publish: results first, then the ring entry.  An entry is only overwritten once its previous occupant
+                // (J - RING, claimed long ago) has finished, so "ring[J % RING] >= J + 1" always means "J is done".
+                STAT_T0();
+                if (lane == 0) {
+                    volatile unsigned* slot = &sh.ring[J & (TELEA_RING - 1)];
+                    while (J >= (unsigned)TELEA_RING && *slot < J - (unsigned)TELEA_RING + 1u) __nanosleep(20);
+                    __threadfence_block();
+                    *slot = J + 1u;
+                    atomicAdd(&sh.done_t, 1);
+                }
+                __syncwarp();
+                STAT_T1(c_rel);
+            }
             STAT_ADD(c_pop);
         }
         __syncthreads();
         if (tid == 0) {
             sh.gbase = gbase + ncur; sh.npool = carry + ntask; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.done_t = 0; sh.tmin = 0xffffffffu;
+            sh.tbase += (unsigned)ntask;
         }
         src ^= 1;
         __syncthreads();
@@ -772,13 +814,15 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32, 4) telea_cluster_kernel(cons
     __shared__ MarchShared sh;
     __shared__ TapTable tp;
     if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
+    for (int i = threadIdx.x; i < TELEA_RING; i += blockDim.x) sh.ring[i] = 0u;
+    if (threadIdx.x == 0) sh.tbase = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int v = blockIdx.y;
+    const int v = blockIdx.x;       // view-major launch order: the first CTAs to start take each view's biggest cluster
     const TeleaView& V = a.v[v];
     const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
     if (V.fs->qbump[V.vi] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
-        if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(&V.fs->overflow, V.fs->qbump[V.vi]);
+        if (threadIdx.x == 0 && blockIdx.y == 0) atomicMax(&V.fs->overflow, V.fs->qbump[V.vi]);
         return;
     }
     Marcher mc{V, a.Hs, a.Ws, lane, &sh.win[threadIdx.x >> 5], &tp, 0, 0};
@@ -792,6 +836,16 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32, 4) telea_cluster_kernel(cons
         const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
         const int* tiles = V.tile_list + V.cl_toff[ci];
         if (threadIdx.x == 0) sh.need_left = V.cl_size[ci];
+#ifdef VSC_EXPERIMENT_SLEEP_MARCH
+        {   // experiment: hold the CTA's resources for about as long as the march would take, without issuing work
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long dur = (unsigned long long)V.cl_size[ci] * VSC_EXPERIMENT_SLEEP_MARCH;
+            do { __nanosleep(100000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < dur);
+            __syncthreads();
+            continue;
+        }
+#endif
         march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 0) * 16 : nullptr);
         __syncthreads();
         march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 1) * 16 : nullptr);
