@@ -762,7 +762,9 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
             if (lane == 0) mc.set_T(y, x, dist);
             __syncwarp();
             STAT_INC(n_pix, 1);
+#ifndef VSC_EXPERIMENT_NO_INPAINT
             if (!OUTER) { STAT_T0(); mc.inpaint(y, x, dist); STAT_T1(c_inp); }
+#endif
             if (lane == 0) {
                 const unsigned char s = mc.S(y, x);
                 mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
@@ -810,7 +812,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
 #endif
 }
 
-__global__ void __launch_bounds__(TELEA_WARPS * 32, 4) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
+__global__ void __launch_bounds__(TELEA_WARPS * 32, 1024 / (TELEA_WARPS * 32)) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
     __shared__ MarchShared sh;
     __shared__ TapTable tp;
     if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
