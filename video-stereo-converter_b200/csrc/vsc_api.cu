@@ -474,7 +474,8 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
     if (g.blur_k > 0) {
         GaussTaps gt = gauss_taps(g.blur_k, p.edge_softness);
         const int r = g.blur_k / 2, AH = DF_T + 2 * r;
-        const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4;
+        // upsampled tile + horizontally blurred tile (also the staging area of the separable upsample) + row taps
+        const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4 + (size_t)AH * sizeof(AxisTap);
         dim3 grid((g.ss_w + DF_T - 1) / DF_T, (g.ss_h + DF_T - 1) / DF_T);
         prof_begin(s, "depth_front_kernel");
         if (g.blur_k == 31)
