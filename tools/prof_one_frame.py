@@ -10,7 +10,7 @@ h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1080, 192
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 G = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 dt = np.uint16 if h > 1080 else np.uint8
-gen = StereoGenerator('cuda', 1, G)
+gen = StereoGenerator('cuda', int(os.environ.get('SLOTS', '2')), G)    # >= 2 slots: the throughput configuration of the march
 frames = [make_pair(h, w, seed=i, depth_dtype=dt) for i in range(max(2, G))]
 d_rgb = [torch.from_numpy(r).cuda() for r, _ in frames]
 d_dep = [torch.from_numpy(d).cuda() for _, d in frames]

@@ -629,7 +629,10 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
     // first CTAs to start take each view's biggest cluster
     dim3 cgrid(nviews, ctx->sm_count / 2);
     prof_begin(s, "telea_cluster_kernel");
-    telea_cluster_kernel<<<cgrid, TELEA_WARPS * 32, 0, s.stream>>>(a);
+    if (ctx->slots.size() == (size_t)ctx->group_size)     // one slot: nothing overlaps the march, favour its latency
+        telea_cluster_kernel<TELEA_WARPS_LATENCY><<<cgrid, TELEA_WARPS_LATENCY * 32, 0, s.stream>>>(a);
+    else
+        telea_cluster_kernel<TELEA_WARPS_THROUGHPUT><<<cgrid, TELEA_WARPS_THROUGHPUT * 32, 0, s.stream>>>(a);
     KCHECK(s);
 #endif
     return VSC_OK;

@@ -495,10 +495,10 @@ __device__ void block_sort(unsigned long long* key, unsigned* idx, int n) {
     }
 }
 
-#ifndef VSC_TELEA_WARPS
-#define VSC_TELEA_WARPS 8
-#endif
-constexpr int TELEA_WARPS = VSC_TELEA_WARPS;
+// Warps per march CTA (template parameter NW of the kernel).  Measured on a B200 at 1080p: with many frames in
+// flight 8 warps give the best throughput (4 / 6 / 8 / 12 warps: 572 / 585 / 604 / 559 frames/s); a single frame
+// alone finishes sooner with 16 (22 ms vs 35 ms), which is what a context with one slot gets.
+constexpr int TELEA_WARPS_THROUGHPUT = 8, TELEA_WARPS_LATENCY = 16;
 // Two compute tasks of one generation whose pixels are closer than this (Chebyshev) run in queue order;
 // farther apart they commute.  Inpainting a pixel reads flags / T / colours within 4 of it and writes only
 // the pixel itself -> 4.  An outer-ring distance reads the 4-neighbours and writes the pixel -> 1.
@@ -506,15 +506,15 @@ constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
 
 constexpr int TELEA_RING = 128;       // completion ring entries (>= tasks in flight, see march)
 constexpr int TELEA_MAXDEP = 32;      // compact dependency list per warp (one entry per lane); more (rare): per-lane polling
-struct MarchShared {
+template <int NW> struct MarchShared {
     int npool, npool2, ncur, ntask, next_t, done_t, gbase, scan_total, need_left;
     unsigned tmin;
     unsigned tbase;                    // CTA-monotonic index of the current generation's first task
     int ci;
-    int wsum[TELEA_WARPS];
+    int wsum[NW];
     unsigned ring[TELEA_RING];         // ring[J % RING] = J + 1 once task J has finished (monotonic per entry)
-    unsigned wdep[TELEA_WARPS][TELEA_MAXDEP];
-    WarpWin win[TELEA_WARPS];
+    unsigned wdep[NW][TELEA_MAXDEP];
+    WarpWin win[NW];
 #ifdef VSC_TELEA_STATS
     unsigned long long c_wait, c_pop, c_sort, c_part, c_total, n_pops, n_pix, n_gen, n_polls, c_load, c_inp, c_rel, c_min4;
 #endif
@@ -543,8 +543,8 @@ __device__ __forceinline__ bool ps_is_task(unsigned v) { return (v & 3u) == 2u; 
 //    belongs to which task), compacted into a short per-warp list, and then polled in the shared-memory
 //    completion ring - a handful of instructions per poll instead of a sweep over global memory.
 //  * the FIFO tie-break of the reference's queue is the task index J, i.e. the sequential push order.
-template <bool OUTER>
-__device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff, int ntiles, const int* tiles, int tw,
+template <bool OUTER, int NW>
+__device__ void march(Marcher& mc, const TeleaView& V, MarchShared<NW>& sh, int qoff, int ntiles, const int* tiles, int tw,
                       int keep_x0, int keep_x1, unsigned long long* stats) {
     unsigned long long* pk[2] = {V.qkey[0] + qoff, V.qkey[1] + qoff};
     unsigned* pi[2] = {V.qidx[0] + qoff, V.qidx[1] + qoff};
@@ -572,7 +572,7 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
 #endif
     __syncthreads();
     // initial queue: the band pixels, T = 0, ordered by raster position (= linear index in the key)
-    for (int ti = wid; ti < ntiles; ti += TELEA_WARPS) {
+    for (int ti = wid; ti < ntiles; ti += NW) {
         const int t = tiles[ti];
         const int ty = t / tw, tx = t - ty * tw;
 #pragma unroll
@@ -812,8 +812,9 @@ __device__ void march(Marcher& mc, const TeleaView& V, MarchShared& sh, int qoff
 #endif
 }
 
-__global__ void __launch_bounds__(TELEA_WARPS * 32, 1024 / (TELEA_WARPS * 32)) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
-    __shared__ MarchShared sh;
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1024 / (NW * 32)) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
+    __shared__ MarchShared<NW> sh;
     __shared__ TapTable tp;
     if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
     for (int i = threadIdx.x; i < TELEA_RING; i += blockDim.x) sh.ring[i] = 0u;
@@ -848,9 +849,9 @@ __global__ void __launch_bounds__(TELEA_WARPS * 32, 1024 / (TELEA_WARPS * 32)) t
             continue;
         }
 #endif
-        march<true>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 0) * 16 : nullptr);
+        march<true, NW>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 0) * 16 : nullptr);
         __syncthreads();
-        march<false>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 1) * 16 : nullptr);
+        march<false, NW>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 1) * 16 : nullptr);
         __syncthreads();
     }
 }
