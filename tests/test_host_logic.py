@@ -60,6 +60,38 @@ def test_in_order_publisher(tmp_path):
     assert not list(tmp_path.glob('*.ready')) and not list(tmp_path.glob('.*.part'))
 
 
+def test_raw_frame_sink_writes_in_clip_order(tmp_path):
+    """frames arrive out of order from several workers, the stream is in clip order."""
+    import threading
+    n, h, w = 40, 3, 8
+    path = str(tmp_path / 'sbs.rgb')
+    sink = sharder.RawFrameSink(path, n, h, w, max_ahead=6, frame_numbers=range(100, 100 + n))
+
+    def worker(ids):
+        for i in ids:
+            sink.put(i, np.full((h, w, 3), i, np.uint8))
+    ths = [threading.Thread(target=worker, args=(list(range(k, n, 3)),)) for k in range(3)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert sink.close() and sink.written == n
+    data = np.fromfile(path, np.uint8).reshape(n, h, w, 3)
+    assert (data == np.arange(n, dtype=np.uint8)[:, None, None, None]).all()
+    meta = json.loads(open(path + '.json').read())
+    assert meta['pix_fmt'] == 'rgb24' and (meta['width'], meta['height'], meta['frames']) == (w, h, n)
+    assert meta['frame_numbers'][0] == 100 and meta['bytes_per_frame'] == h * w * 3
+    with pytest.raises(ValueError):
+        sharder.RawFrameSink(str(tmp_path / 'x.rgb'), 1, h, w).put(0, np.zeros((h, w), np.uint8))
+
+
+def test_raw_frame_sink_stops_at_a_gap(tmp_path):
+    path = str(tmp_path / 'gap.rgb')
+    sink = sharder.RawFrameSink(path, 4, 2, 2)
+    for i in (0, 1, 3):
+        sink.put(i, np.full((2, 2, 3), i, np.uint8))
+    assert sink.close(timeout_s=5) is False and sink.written == 2        # frame 2 never came: the stream ends before it
+    assert os.path.getsize(path) == 2 * 12
+
+
 def _workflow(tmp_path, stereo=None, n=3):
     wf = tmp_path / 'wf'
     for d in ('frames', 'depth_maps', 'sbs'):

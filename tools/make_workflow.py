@@ -14,8 +14,14 @@ cfg = {'input_video': 'in.mkv', 'output_video': 'out.mkv',
        'depth': {'save_16bit': True}, 'encoding': {'crf': 19, 'preset': 'slow'},
        'free_space': {'sbs_generator': 'none', 'chunk_generator': 'none'}}
 json.dump(cfg, open(os.path.join(wf, 'config.json'), 'w'))
+distinct = int(sys.argv[5]) if len(sys.argv) > 5 else n      # frames beyond `distinct` are symlinks to the first ones
 for i in range(n):
+    fp, dp = os.path.join(wf, 'frames', f'frame_{i:06d}.png'), os.path.join(wf, 'depth_maps', f'depth_frame_{i:06d}.tif')
+    if i >= distinct:
+        os.symlink(os.path.join(wf, 'frames', f'frame_{i % distinct:06d}.png'), fp)
+        os.symlink(os.path.join(wf, 'depth_maps', f'depth_frame_{i % distinct:06d}.tif'), dp)
+        continue
     rgb, depth = make_pair(h, w, seed=i % 8, depth_dtype=np.uint16)
-    cv2.imwrite(os.path.join(wf, 'frames', f'frame_{i:06d}.png'), cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
-    cv2.imwrite(os.path.join(wf, 'depth_maps', f'depth_frame_{i:06d}.tif'), depth)
+    cv2.imwrite(fp, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+    cv2.imwrite(dp, depth)
 print('workflow', wf, n, 'frames', w, 'x', h)

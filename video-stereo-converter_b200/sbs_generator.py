@@ -49,12 +49,17 @@ def build_parser() -> ArgumentParser:
     p.add_argument('--gpus', type=int, default=0, help='number of GPUs to shard the clip over (0 = all visible, or the torchrun world)')
     p.add_argument('--slots', type=int, default=6, help='frames in flight per GPU')
     p.add_argument('--io-threads', type=int, default=8, help='loader and saver threads per GPU')
+    p.add_argument('--raw-sink', default=None, metavar='PATH',
+                   help="hand the SBS frames to an encoder instead of writing sbs_*.png: raw rgb24, in clip order, into PATH "
+                        "(a file or FIFO; '-' = stdout); geometry in PATH.json.  Processes every frame pair (no resume)")
     return p
 
 
 def process_shard(pairs, output_dir: Path, params, device_index: int, slots: int, io_threads: int, free_space_mode: str,
-                  no_interactive: bool, progress=None) -> int:
-    """Run `pairs` [(frame_path, depth_path, frame_num)] through one GPU.  Returns frames written."""
+                  no_interactive: bool, progress=None, sink=None, sink_index=None) -> int:
+    """Run `pairs` [(frame_path, depth_path, frame_num)] through one GPU.  Returns frames written.
+    With `sink` (a RawFrameSink shared by all GPUs of the process) frames go to it at position
+    `sink_index[frame_num]` instead of into sbs_<n>.png."""
     import cv2
     import numpy as np
     from vsc_b200 import StereoGenerator, load_image_pair
@@ -75,6 +80,18 @@ def process_shard(pairs, output_dir: Path, params, device_index: int, slots: int
             return None
 
     def save(sbs, item):
+        if sink is not None:
+            try:
+                sink.put(sink_index[item[2]], sbs)
+            except Exception as e:
+                print(f'\nRaw sink failed at SBS frame #{item[2]}: {e}')
+                save_failed.set()
+                return
+            with lock:
+                written[0] += 1
+            if progress:
+                progress(item)
+            return
         final = str(output_dir / f'sbs_{item[2]}.png')
         staged = InOrderPublisher.staged_path(final)
         for attempt in range(3):        # reference: 3 retries, 60 s apart (sbs_generator.py:241-262)
@@ -113,6 +130,8 @@ def process_shard(pairs, output_dir: Path, params, device_index: int, slots: int
                 prefetch.append(loaders.submit(load, pairs[nxt_load]))
                 nxt_load += 1
             if loaded is None:
+                if sink is not None:
+                    sink.skip(sink_index[item[2]])      # keep the stream gap-free
                 continue
             if save_failed.is_set():
                 break
@@ -143,6 +162,8 @@ def process_shard(pairs, output_dir: Path, params, device_index: int, slots: int
 
 def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
+    if args.raw_sink == '-':
+        sys.stdout = sys.stderr          # stdout carries the frames
     if not args.workflow_path.is_dir():
         print(f'ERROR: Workflow directory not found: {args.workflow_path}')
         return 0
@@ -179,7 +200,7 @@ def main(argv=None) -> int:
     all_pairs, missing, first, last = find_frame_pairs(frames_dir, depth_dir)
     if missing and rank == 0:
         print(f'Missing depth maps: {missing} of {missing + len(all_pairs)} frames in range of frame_{first} to frame_{last}')
-    pairs = [p for p in all_pairs if not (output_dir / f'sbs_{p[2]}.png').exists()]
+    pairs = [p for p in all_pairs if args.raw_sink or not (output_dir / f'sbs_{p[2]}.png').exists()]
     skipped = len(all_pairs) - len(pairs)
     if rank == 0:
         print(f'Found: {len(all_pairs)} frame pairs, {skipped} already processed, {len(pairs)} to process')
@@ -201,6 +222,19 @@ def main(argv=None) -> int:
               f'smoothing={params.artifact_smoothing}, gamma={params.depth_gamma}, sharpen={params.sharpen}')
 
     finals = [str(output_dir / f'sbs_{p[2]}.png') for p in pairs]
+    sink = sink_index = None
+    if args.raw_sink:
+        if world > 1:
+            print('ERROR: --raw-sink needs all GPUs in one process (use --gpus N, not torchrun)')
+            return 2
+        import cv2
+        from vsc_b200.sharder import RawFrameSink
+        probe = cv2.imread(str(pairs[0][0]), cv2.IMREAD_COLOR)
+        if probe is None:
+            print(f'ERROR: cannot read {pairs[0][0]}')
+            return 0
+        sink = RawFrameSink(args.raw_sink, len(pairs), probe.shape[0], 2 * probe.shape[1], frame_numbers=[p[2] for p in pairs])
+        sink_index = {p[2]: i for i, p in enumerate(pairs)}
     t0 = time.time()
     done = [0]
 
@@ -229,11 +263,12 @@ def main(argv=None) -> int:
         else:
             g = args.gpus or ngpu
             g = max(1, min(g, ngpu, len(pairs)))
-            pub = InOrderPublisher(finals)
+            pub = InOrderPublisher([] if sink is not None else finals)
             t = threading.Thread(target=pub.run, daemon=True)
             t.start()
             if g == 1:
-                n = process_shard(pairs, output_dir, params, 0, args.slots, args.io_threads, free_space_mode, args.no_interactive, progress)
+                n = process_shard(pairs, output_dir, params, 0, args.slots, args.io_threads, free_space_mode, args.no_interactive, progress,
+                                  sink, sink_index)
             else:
                 # one worker thread per GPU; each owns a StereoGenerator (its own CUDA context state, streams, pinned ring)
                 results = [0] * g
@@ -242,7 +277,7 @@ def main(argv=None) -> int:
                 def work(k):
                     try:
                         results[k] = process_shard(shard_items(pairs, g, k), output_dir, params, k, args.slots, args.io_threads,
-                                                   free_space_mode, args.no_interactive, progress)
+                                                   free_space_mode, args.no_interactive, progress, sink, sink_index)
                     except BaseException as e:   # noqa: BLE001
                         errors.append(e)
                 ths = [threading.Thread(target=work, args=(k,)) for k in range(g)]
@@ -254,6 +289,8 @@ def main(argv=None) -> int:
                     raise errors[0]
                 n = sum(results)
             pub.run(timeout_s=600)
+            if sink is not None and not sink.close():
+                print(f'\nWARNING: raw sink holds {sink.written} of {len(pairs)} frames (stream ends at the first missing frame)')
     except VscCudaError as e:
         print(f'\nERROR: GPU failure - {e}')
         return GPU_ERROR_EXIT_CODE

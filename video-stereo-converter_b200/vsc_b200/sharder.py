@@ -21,7 +21,8 @@ import threading
 import time
 from typing import Callable, List, Optional, Sequence, Tuple
 
-__all__ = ['contiguous_ranges', 'block_cyclic', 'shard_items', 'InOrderPublisher', 'dist_env', 'barrier', 'all_reduce_max']
+__all__ = ['contiguous_ranges', 'block_cyclic', 'shard_items', 'InOrderPublisher', 'RawFrameSink', 'dist_env', 'barrier',
+           'all_reduce_max']
 
 
 def contiguous_ranges(n: int, world: int) -> List[Tuple[int, int]]:
@@ -110,6 +111,97 @@ class InOrderPublisher:
 
     def stop(self) -> None:
         self._stop.set()
+
+
+class RawFrameSink:
+    """In-order hand-off of packed SBS frames to an encoder, skipping the `sbs_*.png` intermediate
+    (the consumer today is chunk_generator.py:241-254, which re-decodes the PNGs
+    and feeds libx265).
+
+    Worker threads `put(index, frame)` finished frames in any order; one writer thread emits them strictly
+    in clip order as raw `rgb24` into a single byte stream (a file, a FIFO an encoder reads from, or '-'
+    for stdout), e.g.
+
+        ffmpeg -f rawvideo -pix_fmt rgb24 -s 3840x1080 -r 24 -i sbs.rgb -c:v libx265 ... out.mkv
+
+    A JSON side-car (`<path>.json`, not written for '-') records the geometry and the frame numbers.
+    `put` blocks while a frame is more than `max_ahead` positions ahead of the write cursor, so memory
+    stays bounded when one GPU runs ahead of another.
+    """
+
+    def __init__(self, path: str, n_frames: int, height: int, width: int, max_ahead: int = 256, frame_numbers=None):
+        import json
+        self.path, self.n, self.h, self.w = str(path), int(n_frames), int(height), int(width)
+        self.max_ahead = int(max_ahead)
+        self._pending = {}
+        self._next = 0
+        self._cv = threading.Condition()
+        self._error: Optional[BaseException] = None
+        self._closed = False
+        if self.path == '-':
+            import sys
+            self._f = sys.__stdout__.buffer     # the driver moves its own messages to stderr in this mode
+        else:
+            self._f = open(self.path, 'wb')
+            with open(self.path + '.json', 'w') as jf:
+                json.dump({'pix_fmt': 'rgb24', 'width': self.w, 'height': self.h, 'frames': self.n,
+                           'bytes_per_frame': self.w * self.h * 3,
+                           'frame_numbers': list(frame_numbers) if frame_numbers is not None else None,
+                           'ffmpeg_input': f'-f rawvideo -pix_fmt rgb24 -s {self.w}x{self.h} -i {self.path}'}, jf)
+        self._t = threading.Thread(target=self._run, name='raw-sink', daemon=True)
+        self._t.start()
+
+    def put(self, index: int, frame) -> None:
+        if frame.shape != (self.h, self.w, 3) or str(frame.dtype) != 'uint8':
+            raise ValueError(f'frame {index}: expected uint8 {(self.h, self.w, 3)}, got {frame.dtype} {frame.shape}')
+        with self._cv:
+            while index - self._next > self.max_ahead and self._error is None:
+                self._cv.wait(0.1)
+            if self._error is not None:
+                raise RuntimeError(f'raw sink failed: {self._error}')
+            self._pending[int(index)] = frame
+            self._cv.notify_all()
+
+    def skip(self, index: int) -> None:
+        """A frame that could not be produced (load error): keep the stream gap-free with a black frame."""
+        import numpy as np
+        self.put(index, np.zeros((self.h, self.w, 3), np.uint8))
+
+    @property
+    def written(self) -> int:
+        return self._next
+
+    def _run(self) -> None:
+        try:
+            while True:
+                with self._cv:
+                    while self._next not in self._pending:
+                        if self._closed or self._next >= self.n:
+                            return
+                        self._cv.wait(0.1)
+                    frame = self._pending.pop(self._next)
+                self._f.write(memoryview(frame).cast('B') if frame.flags['C_CONTIGUOUS'] else frame.tobytes())
+                with self._cv:
+                    self._next += 1
+                    self._cv.notify_all()
+        except BaseException as e:   # noqa: BLE001  (a broken pipe must reach the producers)
+            with self._cv:
+                self._error = e
+                self._cv.notify_all()
+
+    def close(self, timeout_s: float = 600.0) -> bool:
+        """Write out everything that is contiguous with the cursor, then stop.  True if the whole clip was written."""
+        with self._cv:
+            self._closed = True       # the writer keeps going while the next frame is there and stops at the first gap
+            self._cv.notify_all()
+        self._t.join(timeout=timeout_s)
+        if self.path != '-':
+            self._f.close()
+        else:
+            self._f.flush()
+        if self._error is not None:
+            raise RuntimeError(f'raw sink failed: {self._error}')
+        return self._next >= self.n
 
 
 # ---- torch.distributed plumbing (NCCL on GPUs, gloo in CPU tests); no data-path collective -------------
