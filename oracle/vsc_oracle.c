@@ -295,54 +295,85 @@ ORC_API void orc_gauss_blur(const float *src, int C, int H, int W, int k, const 
 
 /* ------------------------------------------------------------------------------------------
  * apply_depth_gamma (stereo_core.py:91-107): pow(clamp(d,0.001,1), gamma).
- * Deterministic pow shared (by specification, not by code) with the CUDA path:
- *   x = m * 2^e, m in [sqrt(1/2), sqrt(2)); log2(x) = e + log2(m) via atanh series in double;
- *   2^t = 2^n * exp(ln2 * f), n = rint(t), Taylor/Horner in double; result rounded to f32.
- * Only +,*,fma and one division in double => identical bits on any IEEE-754 machine.
+ * Deterministic pow shared (by specification, not by code) with the CUDA path.  Table-driven, no division:
+ *   x = m * 2^e, m in [1,2); i = top 7 mantissa bits, c_i = 1 + (i + 1/2)/128;
+ *   r = fma(m, 1/c_i, -1)  (|r| < 2^-8);  ln(1+r) = r * Horner(1, -1/2, 1/3, -1/4, 1/5, -1/6, 1/7);
+ *   log2(x) = fma(ln(1+r), log2(e), e + log2(c_i));
+ *   t = g * log2(x); k = rint(64 t), j = k mod 64, n = (k - j)/64; f = (t - k/64) * ln2  (|f| < 2^-7.5);
+ *   2^t = ldexp(2^(j/64) * Horner(1, 1, 1/2, 1/6, 1/24, 1/120), n); result rounded to f32.
+ * The three tables (1/c_i, log2 c_i, 2^(j/64)) are themselves computed with a fixed series (below), so every
+ * number is the result of IEEE-754 +,*,/,fma only => identical bits on any conforming machine, CPU or GPU.
+ * The double result is accurate to ~1e-16, i.e. the float is correctly rounded except for ~1e-7 of inputs.
  * ---------------------------------------------------------------------------------------- */
-static double det_log2(double x) {
+static double tab_log2(double x) { /* series used for the tables only: atanh series of ln(m), m in [sqrt(1/2), sqrt(2)) */
     int e;
-    double m = frexp(x, &e); /* m in [0.5,1) */
+    double m = frexp(x, &e);
     if (m < 0.70710678118654752440) { m *= 2.0; e -= 1; }
     double s = (m - 1.0) / (m + 1.0);
     double z = s * s;
-    /* atanh series: ln(m) = 2*(s + s^3/3 + s^5/5 + ...); |s| <= 0.1716 -> 13 terms ~ 1e-21 */
     double p = 1.0 / 27.0;
-    p = fma(p, z, 1.0 / 25.0);
-    p = fma(p, z, 1.0 / 23.0);
-    p = fma(p, z, 1.0 / 21.0);
-    p = fma(p, z, 1.0 / 19.0);
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, 1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, 1.0 / 3.0);
-    p = fma(p, z, 1.0);
+    for (int d = 25; d >= 1; d -= 2) p = fma(p, z, 1.0 / (double)d);
     double ln_m = 2.0 * s * p;
     return fma(ln_m, 1.4426950408889634074, (double)e);
 }
-
-static double det_exp2(double t) {
+static double tab_exp2(double t) { /* tables only: Taylor series of exp(ln2 * f), |f| <= 1/2 */
     double n = nearbyint(t);
-    double f = (t - n) * 0.69314718055994530942; /* |f| <= 0.3466 */
-    double p = 1.0 / 6227020800.0; /* 1/13! */
-    p = fma(p, f, 1.0 / 479001600.0);
-    p = fma(p, f, 1.0 / 39916800.0);
-    p = fma(p, f, 1.0 / 3628800.0);
-    p = fma(p, f, 1.0 / 362880.0);
-    p = fma(p, f, 1.0 / 40320.0);
-    p = fma(p, f, 1.0 / 5040.0);
-    p = fma(p, f, 1.0 / 720.0);
-    p = fma(p, f, 1.0 / 120.0);
+    double f = (t - n) * 0.69314718055994530942;
+    static const double inv_fact[14] = {1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                                        1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                                        1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p = inv_fact[13];
+    for (int d = 12; d >= 0; d--) p = fma(p, f, inv_fact[d]);
+    return ldexp(p, (int)n);
+}
+static double pw_invc[128], pw_log2c[128], pw_exp2t[64];
+static int pw_ready;
+static void pw_init(void) {
+    if (pw_ready) return;
+#pragma omp critical(orc_pw_init)
+    if (!pw_ready) {
+        for (int i = 0; i < 128; i++) {
+            const double c = 1.0 + ((double)i + 0.5) / 128.0;
+            pw_invc[i] = 1.0 / c;
+            pw_log2c[i] = tab_log2(c);
+        }
+        for (int j = 0; j < 64; j++) pw_exp2t[j] = tab_exp2((double)j / 64.0);
+        pw_ready = 1;
+    }
+}
+ORC_API void orc_pow_tables(double *invc, double *log2c, double *exp2t) { /* for tests: the tables of the specification */
+    pw_init();
+    memcpy(invc, pw_invc, sizeof pw_invc); memcpy(log2c, pw_log2c, sizeof pw_log2c); memcpy(exp2t, pw_exp2t, sizeof pw_exp2t);
+}
+static double det_log2(double x) { /* x normal, positive */
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    const int e = (int)((b >> 52) & 0x7ff) - 1023, i = (int)((b >> 45) & 127);
+    b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m;
+    memcpy(&m, &b, 8);
+    const double r = fma(m, pw_invc[i], -1.0);
+    double q = 1.0 / 7.0;
+    q = fma(q, r, -1.0 / 6.0);
+    q = fma(q, r, 1.0 / 5.0);
+    q = fma(q, r, -1.0 / 4.0);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -1.0 / 2.0);
+    q = fma(q, r, 1.0);
+    const double ln1p = r * q;
+    return fma(ln1p, 1.4426950408889634074, (double)e + pw_log2c[i]);
+}
+static double det_exp2(double t) {
+    const double k = nearbyint(t * 64.0);
+    const int ki = (int)k, j = ki & 63, n = (ki - j) / 64;
+    const double f = (t - k * 0.015625) * 0.69314718055994530942;
+    double p = 1.0 / 120.0;
     p = fma(p, f, 1.0 / 24.0);
     p = fma(p, f, 1.0 / 6.0);
     p = fma(p, f, 0.5);
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
-    return ldexp(p, (int)n);
+    return ldexp(pw_exp2t[j] * p, n);
 }
 
 ORC_API float orc_powf(float x, float g) {
@@ -350,10 +381,12 @@ ORC_API float orc_powf(float x, float g) {
     if (g == 2.0f) return x * x;
     if (g == 3.0f) return (x * x) * x;
     if (x == 1.0f) return 1.0f;
+    pw_init();
     return (float)det_exp2((double)g * det_log2((double)x));
 }
 
 ORC_API void orc_gamma(const float *d, size_t n, float gamma, float *out) {
+    pw_init();
 #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; i++) {
         float v = d[i];

@@ -275,7 +275,38 @@ struct vsc_ctx {
     int sm_count = 148;
     std::vector<Slot> slots;
     DevBuf color_w;     // bilateral colour LUT for sigmaColor = 30 (stereo_core.py:410)
+    DevBuf pow_tab;     // tables of the deterministic pow (apply_depth_gamma)
 };
+
+// The pow tables of the specification (oracle/vsc_oracle.c: tab_log2 / tab_exp2 / pw_init), computed with the same
+// fixed series in IEEE double (this file is compiled with -ffp-contract=off; fma() is the correctly rounded one).
+static double tab_log2(double x) {
+    int e;
+    double m = frexp(x, &e);
+    if (m < 0.70710678118654752440) { m *= 2.0; e -= 1; }
+    const double s = (m - 1.0) / (m + 1.0), z = s * s;
+    double p = 1.0 / 27.0;
+    for (int d = 25; d >= 1; d -= 2) p = fma(p, z, 1.0 / (double)d);
+    const double ln_m = 2.0 * s * p;
+    return fma(ln_m, 1.4426950408889634074, (double)e);
+}
+static double tab_exp2(double t) {
+    const double n = nearbyint(t), f = (t - n) * 0.69314718055994530942;
+    static const double inv_fact[14] = {1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                                        1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                                        1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p = inv_fact[13];
+    for (int d = 12; d >= 0; d--) p = fma(p, f, inv_fact[d]);
+    return ldexp(p, (int)n);
+}
+static void pow_tables(double* tab) {
+    for (int i = 0; i < 128; i++) {
+        const double c = 1.0 + ((double)i + 0.5) / 128.0;
+        tab[i] = 1.0 / c;
+        tab[128 + i] = tab_log2(c);
+    }
+    for (int j = 0; j < 64; j++) tab[256 + j] = tab_exp2((double)j / 64.0);
+}
 
 static int upload_constants(vsc_ctx* ctx) {
     TapConst tc;
@@ -296,6 +327,10 @@ static int upload_constants(vsc_ctx* ctx) {
     bilateral_tables(5, 30.0, 25.0, cw, bt);
     if (ctx->color_w.ensure(sizeof cw)) return VSC_E_NOMEM;
     CU(cudaMemcpy(ctx->color_w.p, cw, sizeof cw, cudaMemcpyHostToDevice));
+    double pt[kPowTabN];
+    pow_tables(pt);
+    if (ctx->pow_tab.ensure(sizeof pt)) return VSC_E_NOMEM;
+    CU(cudaMemcpy(ctx->pow_tab.p, pt, sizeof pt, cudaMemcpyHostToDevice));
     return VSC_OK;
 }
 
@@ -377,6 +412,7 @@ extern "C" void vsc_destroy(vsc_ctx* ctx) {
         if (s.stream && s.owns_stream) cudaStreamDestroy(s.stream);
     }
     ctx->color_w.release();
+    ctx->pow_tab.release();
     delete ctx;
 }
 extern "C" int vsc_device(const vsc_ctx* ctx) { return ctx ? ctx->device : -1; }
@@ -474,21 +510,21 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
     if (g.blur_k > 0) {
         GaussTaps gt = gauss_taps(g.blur_k, p.edge_softness);
         const int r = g.blur_k / 2, AH = DF_T + 2 * r;
-        // upsampled tile + horizontally blurred tile (also the staging area of the separable upsample) + row taps
-        const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4 + (size_t)AH * sizeof(AxisTap);
+        // upsampled tile + horizontally blurred tile (also the staging area of the separable upsample) + row taps + pow tables
+        const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4 + (size_t)AH * sizeof(AxisTap) + kPowTabN * sizeof(double);
         dim3 grid((g.ss_w + DF_T - 1) / DF_T, (g.ss_h + DF_T - 1) / DF_T);
         prof_begin(s, "depth_front_kernel");
         if (g.blur_k == 31)
             depth_front_kernel<31><<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
-                                                                       g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
+                                                                       g.super_sampled, gt, gamma, apply_gamma, ctx->pow_tab.as<double>(), d_depth_ss);
         else
             depth_front_kernel<0><<<grid, kThreads, smem, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
-                                                                      g.super_sampled, gt, gamma, apply_gamma, d_depth_ss);
+                                                                      g.super_sampled, gt, gamma, apply_gamma, ctx->pow_tab.as<double>(), d_depth_ss);
     } else {
         dim3 grid((g.ss_w + kThreads * 4 - 1) / (kThreads * 4), g.ss_h);
         prof_begin(s, "depth_point_kernel");
         depth_point_kernel<<<grid, kThreads, 0, s.stream>>>(d_depth_st, g.stretched_w, g.ss_h, g.ss_w, s.d_ty, s.d_tx,
-                                                            g.super_sampled, gamma, apply_gamma, d_depth_ss);
+                                                            g.super_sampled, gamma, apply_gamma, ctx->pow_tab.as<double>(), d_depth_ss);
     }
     KCHECK(s);
     return VSC_OK;
@@ -1087,7 +1123,7 @@ extern "C" int vsc_stage_gamma_f32(vsc_ctx* ctx, const float* in, size_t n, doub
     Tmp d, o;
     if (d.alloc(n * 4) || o.alloc(n * 4)) return VSC_E_NOMEM;
     CU(cudaMemcpyAsync(d.p, in, n * 4, cudaMemcpyHostToDevice, s.stream));
-    gamma_kernel<<<ctx->sm_count * 4, kThreads, 0, s.stream>>>((const float*)d.p, n, (float)gamma, (float*)o.p);
+    gamma_kernel<<<ctx->sm_count * 4, kThreads, 0, s.stream>>>((const float*)d.p, n, (float)gamma, ctx->pow_tab.as<double>(), (float*)o.p);
     CU(cudaMemcpyAsync(out, o.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
     return VSC_OK;

@@ -84,61 +84,45 @@ __device__ __forceinline__ void cta_copy_s2g(uint8_t* __restrict__ g, const uint
 }
 
 // ---- deterministic pow for apply_depth_gamma (stereo_core.py:107) ------------------------------
-// Same specification as the oracle's orc_powf: only IEEE-754 double +,*,/,fma and exact
-// frexp/ldexp/rint, so CPU and GPU agree bit for bit; the result is the double value rounded to
-// float, i.e. correctly rounded except for ~1e-4 of inputs.
-// x is a normal positive double here (a float in [0.001, 1]); frexp / ldexp are exact, so doing them on the
-// exponent field directly gives the same bits as the library calls without their special-case handling
-__device__ __forceinline__ double det_log2(double x) {
+// Same specification as the oracle's orc_powf (oracle/vsc_oracle.c): table-driven log2 / exp2 in double built
+// from IEEE-754 +,*,fma only, so CPU and GPU agree bit for bit; the result is the double value rounded to
+// float (correctly rounded except for ~1e-7 of inputs).  `tab` = [1/c_i (128) | log2 c_i (128) | 2^(j/64) (64)],
+// computed once on the host with the specification's fixed series (vsc_api.cu: pow_tables).
+constexpr int kPowTabN = 320;
+__device__ __forceinline__ double det_log2(double x, const double* tab) {      // x normal, positive
     const int hi = __double2hiint(x);
-    int e = ((hi >> 20) & 0x7ff) - 1022;
-    double m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));    // frexp: m in [0.5, 1)
-    if (m < 0.70710678118654752440) { m = __dmul_rn(m, 2.0); e -= 1; }
-    const double s = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
-    const double z = __dmul_rn(s, s);
-    double p = 1.0 / 27.0;
-    p = fma(p, z, 1.0 / 25.0);
-    p = fma(p, z, 1.0 / 23.0);
-    p = fma(p, z, 1.0 / 21.0);
-    p = fma(p, z, 1.0 / 19.0);
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, 1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, 1.0 / 3.0);
-    p = fma(p, z, 1.0);
-    const double ln_m = __dmul_rn(__dmul_rn(2.0, s), p);
-    return fma(ln_m, 1.4426950408889634074, (double)e);
+    const int e = ((hi >> 20) & 0x7ff) - 1023, i = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));    // [1, 2)
+    const double r = fma(m, tab[i], -1.0);
+    double q = 1.0 / 7.0;
+    q = fma(q, r, -1.0 / 6.0);
+    q = fma(q, r, 1.0 / 5.0);
+    q = fma(q, r, -1.0 / 4.0);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -1.0 / 2.0);
+    q = fma(q, r, 1.0);
+    const double ln1p = __dmul_rn(r, q);
+    return fma(ln1p, 1.4426950408889634074, __dadd_rn((double)e, tab[128 + i]));
 }
-__device__ __forceinline__ double det_exp2(double t) {
-    const double n = rint(t);
-    const double f = __dmul_rn(__dadd_rn(t, -n), 0.69314718055994530942);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, f, 1.0 / 479001600.0);
-    p = fma(p, f, 1.0 / 39916800.0);
-    p = fma(p, f, 1.0 / 3628800.0);
-    p = fma(p, f, 1.0 / 362880.0);
-    p = fma(p, f, 1.0 / 40320.0);
-    p = fma(p, f, 1.0 / 5040.0);
-    p = fma(p, f, 1.0 / 720.0);
-    p = fma(p, f, 1.0 / 120.0);
+__device__ __forceinline__ double det_exp2(double t, const double* tab) {
+    const double k = rint(__dmul_rn(t, 64.0));
+    const int ki = (int)k, j = ki & 63, n = (ki - j) / 64;
+    const double f = __dmul_rn(__dadd_rn(t, -__dmul_rn(k, 0.015625)), 0.69314718055994530942);
+    double p = 1.0 / 120.0;
     p = fma(p, f, 1.0 / 24.0);
     p = fma(p, f, 1.0 / 6.0);
     p = fma(p, f, 0.5);
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
-    const int k = (int)n;
-    if (k < -1000 || k > 1000) return ldexp(p, k);      // would leave the normal range: let the library round
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));          // p in (0.5, 2): exact scaling
+    const double v = __dmul_rn(tab[256 + j], p);
+    if (n < -1000 || n > 1000) return ldexp(v, n);      // would leave the normal range: let the library round
+    return __hiloint2double(__double2hiint(v) + n * 1048576, __double2loint(v));      // exact scaling of a normal number
 }
-__device__ __forceinline__ float det_powf(float x, float g) {
+__device__ __forceinline__ float det_powf(float x, float g, const double* tab) {
     if (g == 2.0f) return __fmul_rn(x, x);
     if (g == 3.0f) return __fmul_rn(__fmul_rn(x, x), x);
     if (x == 1.0f) return 1.0f;
-    return (float)det_exp2(__dmul_rn((double)g, det_log2((double)x)));
+    return (float)det_exp2(__dmul_rn((double)g, det_log2((double)x, tab)), tab);
 }
 
 // ---- TMA bulk copy (cp.async.bulk, 1-D) of a byte range into shared memory ---------------------
