@@ -361,7 +361,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=240, help='frames per step per GPU')
+    ap.add_argument('--batch', type=int, default=300, help='frames per step per GPU (BASELINE.json configs[1]: a 300-frame clip)')
     ap.add_argument('--slots', type=int, default=30, help='slots (CUDA streams) per GPU')
     ap.add_argument('--group', type=int, default=4, help='frames per slot submission (share a stream and one hole-filling launch)')
     ap.add_argument('--cpu-frames', type=int, default=2)

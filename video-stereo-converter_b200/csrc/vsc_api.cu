@@ -477,12 +477,12 @@ static void prof_end(Slot& s) {
 #define KCHECK(s) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(VSC_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); (s).launches++; prof_end(s); } while (0)
 
 // ---- device-level stage launchers (all asynchronous on s.stream) --------------------------------
-static int run_lanczos_rgb(Slot& s, const uint8_t* d_rgb, int H, int W, int SW, uint8_t* d_out) {
+static int run_lanczos_rgb(Slot& s, const uint8_t* d_rgb, int H, int W, int SW, uint8_t* d_out, FrameScalars* reset_fs = nullptr) {
     const int stage = (int)align_up((size_t)W * 3 + 32, 16);
     const size_t smem = stage + align_up((size_t)SW * 3 + 16, 16);
     if (smem > 200 * 1024) return fail(VSC_E_INVALID, "frame width %d too large for the row-staged Lanczos kernel", W);
     prof_begin(s, "lanczos_rgb_kernel");
-    lanczos_rgb_kernel<<<H, kThreads, smem, s.stream>>>(d_rgb, W, SW, s.d_sx0, s.d_it, s.ib3, d_out, stage);
+    lanczos_rgb_kernel<<<H, kThreads, smem, s.stream>>>(d_rgb, W, SW, s.d_sx0, s.d_it, s.ib3, d_out, stage, reset_fs);
     KCHECK(s);
     return VSC_OK;
 }
@@ -737,10 +737,7 @@ static int enqueue_group(vsc_ctx* ctx, Slot* fr, int n, int dtype, const vsc_geo
     for (int i = 0; i < n; i++) {
         Slot& s = fr[i];
         int rc;
-        prof_begin(s, "frame_init_kernel");
-        frame_init_kernel<<<1, 32, 0, s.stream>>>(s.scalars.as<FrameScalars>());
-        KCHECK(s);
-        if ((rc = run_lanczos_rgb(s, s.l_rgb, g.height, g.width, g.stretched_w, s.rgb_st.as<uint8_t>()))) return rc;
+        if ((rc = run_lanczos_rgb(s, s.l_rgb, g.height, g.width, g.stretched_w, s.rgb_st.as<uint8_t>(), s.scalars.as<FrameScalars>()))) return rc;
         if ((rc = run_lanczos_depth(s, s.l_depth, dtype, g.height, g.width, g.stretched_w, s.depth_st.as<float>()))) return rc;
         if ((rc = run_depth_front(ctx, s, g, p, s.depth_st.as<float>(), s.depth_ss.as<float>()))) return rc;
         uchar4* va[2] = {s.viewA[0].as<uchar4>(), s.viewA[1].as<uchar4>()};
