@@ -542,6 +542,7 @@ static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint
     a.R = (int)ceil(max_disparity) + 1;
     const int nseg = (g.ss_w + 1023) / 1024;
     a.TS = (int)align_up((size_t)(g.ss_w + nseg - 1) / nseg, 32);
+    a.nseg = nseg;
     a.mode = mode;
     const int nsrc = a.TS + 2 * a.R + 8;
     const double ratio = a.upsample ? (double)g.stretched_w / (double)g.ss_w : 1.0;
@@ -551,7 +552,7 @@ static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint
     prof_begin(s, "warp_kernel");
     switch (mode) {
         case 0: warp_kernel<0><<<grid, kThreads, smem, s.stream>>>(a); break;
-        case 1: warp_kernel<1><<<grid, kThreads, smem, s.stream>>>(a); break;
+        case 1: warp_kernel<1><<<dim3(std::min(nseg * g.ss_h, 592)), kThreads, smem, s.stream>>>(a); break;   // normally exits at once
         default: warp_kernel<2><<<grid, kThreads, smem, s.stream>>>(a); break;
     }
     KCHECK(s);
