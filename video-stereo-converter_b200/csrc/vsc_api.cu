@@ -278,7 +278,7 @@ struct vsc_ctx {
     DevBuf pow_tab;     // tables of the deterministic pow (apply_depth_gamma)
 };
 
-// The pow tables of the specification (oracle/vsc_oracle.c: tab_log2 / tab_exp2 / pw_init), computed with the same
+// The pow tables of the specification (float order; the CPU oracle has its own copy), computed with the same
 // fixed series in IEEE double (this file is compiled with -ffp-contract=off; fma() is the correctly rounded one).
 static double tab_log2(double x) {
     int e;

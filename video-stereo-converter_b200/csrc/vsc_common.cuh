@@ -84,7 +84,7 @@ __device__ __forceinline__ void cta_copy_s2g(uint8_t* __restrict__ g, const uint
 }
 
 // ---- deterministic pow for apply_depth_gamma (stereo_core.py:107) ------------------------------
-// Same specification as the oracle's orc_powf (oracle/vsc_oracle.c): table-driven log2 / exp2 in double built
+// Same specification as the CPU oracle's orc_powf: table-driven log2 / exp2 in double built
 // from IEEE-754 +,*,fma only, so CPU and GPU agree bit for bit; the result is the double value rounded to
 // float (correctly rounded except for ~1e-7 of inputs).  `tab` = [1/c_i (128) | log2 c_i (128) | 2^(j/64) (64)],
 // computed once on the host with the specification's fixed series (vsc_api.cu: pow_tables).
