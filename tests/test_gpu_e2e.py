@@ -151,6 +151,28 @@ def test_grouped_slots_match_single_frames():
         g.close()
 
 
+def test_results_do_not_depend_on_load():
+    """The hole-filling dataflow must not depend on timing: frames processed while many other frames are in flight
+    (8 slots x 2 frames, several rounds) equal, bit for bit, the same frames processed alone.  The solo context also
+    runs the 16-warp (latency) variant of the march, the loaded one the 8-warp (throughput) variant."""
+    frames = [make_pair(270, 480, seed=s, depth_dtype=np.uint16 if s % 2 else np.uint8) for s in range(10)]
+    single = StereoGenerator('cuda', n_slots=1)
+    ref = [single.process_frame(r, d) for r, d in frames]
+    single.close()
+    g = StereoGenerator('cuda', n_slots=8, group_size=2)
+    try:
+        for _ in range(3):
+            order = [(i * 3) % len(frames) for i in range(3 * len(frames))]
+            outs = g.process_batch([frames[i] for i in order if frames[i][1].dtype == np.uint8])
+            exp = [ref[i] for i in order if frames[i][1].dtype == np.uint8]
+            assert len(outs) == len(exp) and all(np.array_equal(a, b) for a, b in zip(outs, exp))
+            outs = g.process_batch([frames[i] for i in order if frames[i][1].dtype == np.uint16])
+            exp = [ref[i] for i in order if frames[i][1].dtype == np.uint16]
+            assert all(np.array_equal(a, b) for a, b in zip(outs, exp))
+    finally:
+        g.close()
+
+
 def test_ready_and_wait_any(gen):
     frames = [make_pair(90, 160, seed=s) for s in range(5)]
     ref = [gen.process_frame(r, d) for r, d in frames]

@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(kThreads) telea_prepare_kernel(const __grid_co
         const unsigned stw = spread4(mm) * F_INSIDE | spread4(rg) * O_INSIDE | spread4(bb) * ST_BAND0;
         const size_t p = (size_t)yy * a.Ws + xx;
         if (vec) *reinterpret_cast<unsigned*>(V.st + p) = stw;         // Ws % 4 == 0: xx + 3 < Ws and p % 4 == 0
-        else for (int k = 0; k < 4 && xx + k < a.Ws; k++) V.st[p + k] = (unsigned char)(stw >> (8 * k));
+        else if ((a.Ws & 1) == 0) {                                    // Ws even: p even, pixels come in pairs
+            *reinterpret_cast<unsigned short*>(V.st + p) = (unsigned short)stw;
+            if (xx + 2 < a.Ws) *reinterpret_cast<unsigned short*>(V.st + p + 2) = (unsigned short)(stw >> 16);
+        } else for (int k = 0; k < 4 && xx + k < a.Ws; k++) V.st[p + k] = (unsigned char)(stw >> (8 * k));
         if (nn) {
             for (int k = 0; k < 4 && xx + k < a.Ws; k++)
                 if ((nn >> k) & 1u) { V.tt[p + k] = ((bb >> k) & 1u) ? 0.f : 1.0e6f; V.pstate[p + k] = 0xffffffffu; }
