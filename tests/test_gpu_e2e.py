@@ -151,6 +151,36 @@ def test_grouped_slots_match_single_frames():
         g.close()
 
 
+def _sweep_cases(n=28, seed=2024):
+    """Random points of the sbs_tester sliders (reference sbs_tester.py:356-362: ranges and step sizes), mixed sizes / dtypes."""
+    rng = np.random.default_rng(seed)
+    step = lambda lo, hi, st: float(lo + st * rng.integers(0, int(round((hi - lo) / st)) + 1))   # noqa: E731
+    cases = []
+    for i in range(n):
+        kw = dict(max_disparity=step(5, 100, 0.5), convergence=step(-50, 50, 1.0), super_sampling=round(step(1.0, 4.0, 0.1), 1),
+                  edge_softness=step(0, 30, 0.5), artifact_smoothing=round(step(0, 5, 0.1), 1), depth_gamma=round(step(0.1, 2.0, 0.05), 2),
+                  sharpen=step(0, 16, 0.5))
+        h, w = int(rng.integers(40, 110)), int(rng.integers(160, 330))
+        cases.append((h, w, [np.uint8, np.uint16, np.float32][i % 3], kw))
+    return cases
+
+
+@pytest.mark.parametrize('h,w,dt,kw', _sweep_cases())
+def test_tester_slider_sweep_matches_oracle(gen, h, w, dt, kw):
+    """BASELINE.json configs[4] (the sbs_tester parameter sweep), at sizes the oracle finishes quickly: bit-exact, or
+    the same refusal when the convergence crop leaves no valid window."""
+    rgb, depth = make_pair(h, w, seed=h * 1000 + w, depth_dtype=dt)
+    p = StereoParams(**kw)
+    try:
+        want = O.process_frame(rgb, depth, O.Params(**kw))
+    except (RuntimeError, ValueError):
+        with pytest.raises(RuntimeError):
+            gen.process_frame(rgb, depth, p)
+        return
+    got = gen.process_frame(rgb, depth, p)
+    assert got.shape == want.shape and np.array_equal(got, want), (kw, int((got != want).sum()))
+
+
 def test_results_do_not_depend_on_load():
     """The hole-filling dataflow must not depend on timing: frames processed while many other frames are in flight
     (8 slots x 2 frames, several rounds) equal, bit for bit, the same frames processed alone.  The solo context also
