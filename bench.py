@@ -157,7 +157,9 @@ def run_ours(args, rank, world, local_rank):
         pipe.busy = []
 
     from concurrent.futures import ThreadPoolExecutor
-    loaders = ThreadPoolExecutor(max_workers=max(1, group))
+    # loader threads of this rank: never more than its share of the host cores (N ranks share the box)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    loaders = ThreadPoolExecutor(max_workers=max(1, min(group, cores // max(1, world) - 1)))
     for s_ in range(slots):          # allocate the pinned staging buffers outside the timed region
         for k_ in range(group):
             gen.pinned_inputs(s_, H, W, DEPTH_DTYPE, k_)
