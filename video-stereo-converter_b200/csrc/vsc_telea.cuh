@@ -6,14 +6,16 @@
 // written, so its result depends on the global pop order.  That order only matters between pixels
 // that can see each other (window radius 3 + 1 for gradients, outer distance ring radius 3), so the
 // image is decomposed into independent *clusters* of holes:
-//   1. telea_prepare_kernel   pixel-parallel morphology: M = dilate3x3(hole), band, outer ring,
-//                             initial T, 8x8-tile occupancy and "reaches the kept window" flags
+//   1. telea_prepare_kernel   morphology on the warp kernel's hole bitmap (1 bit per pixel): M = dilate3x3(hole),
+//                             band, outer ring, initial T and order words near M, 8x8-tile occupancy and
+//                             "reaches the kept window" counts; one warp per 32x16 tile, no shared memory
 //   2. tile CCL kernels       union-find connected components over occupied 8x8 tiles; holes in
 //                             different components are >= 15 px apart (> 2*range+2 = 8, the analytic
 //                             independence bound), so components can be marched independently
-//   3. telea_cluster_kernel   one warp per cluster runs the literal sequential algorithm (outer
-//                             ring FMM, then the inpainting FMM); the 28 window taps of a pixel are
-//                             evaluated one per lane and accumulated in the reference's raster order
+//   3. telea_cluster_kernel   one CTA per cluster (persistent CTAs pull clusters, big ones first) runs the
+//                             sequential algorithm as an ordered task dataflow (outer ring FMM, then the
+//                             inpainting FMM); the 28 window taps of a pixel are evaluated one per lane and
+//                             accumulated in the reference's raster order
 // The priority queue (sorted list with FIFO ties in OpenCV) is realised as generations: all queued
 // entries with T in [Tmin, Tmin+0.7) are extracted, sorted by (T, push order) and popped in order;
 // anything pushed meanwhile has T >= popped T + 1/sqrt(2) and therefore belongs to a later
@@ -49,7 +51,7 @@ struct TeleaView {
     int* tile_list;            // [ntiles_active]
     unsigned long long* qkey[3];   // two ping-pong pools + the current generation
     unsigned* qidx[3];
-    unsigned* pstate;          // [Hs][Ws] order / completion word per pixel for the dataflow (see march)
+    unsigned* pstate;          // [Hs][Ws] order word per pixel for the dataflow (which pop / task owns it, see march)
     int qcap;
     FrameScalars* fs;          // per-frame counters of the frame this view belongs to
     int vi;                    // 0 = left, 1 = right eye within that frame
@@ -280,7 +282,7 @@ __global__ void telea_cluster_fill_kernel(const __grid_constant__ TeleaArgs a) {
     }
 }
 
-// ---- 3. per-cluster sequential march, one warp per cluster ---------------------------------------
+// ---- 3. per-cluster march: one CTA per cluster, one warp per task -------------------------------------
 struct TapConst { signed char dk[32]; signed char dl[32]; float dst[32]; };
 __constant__ TapConst c_taps;   // 28 taps of the radius-3 disc in k-major raster order (centre excluded)
 
