@@ -584,24 +584,22 @@ static int run_bilateral(vsc_ctx* ctx, Slot& s, int Hs, int Ws, double smoothing
     KCHECK(s);
     return VSC_OK;
 }
-static int ensure_telea(Slot& s, int Hs, int Ws, int nviews) {
+// scratch of one eye of a frame slot; T / order words are skipped when the caller lends dead buffers for them
+static int ensure_telea_view(Slot& s, int v, int Hs, int Ws, bool need_tt, bool need_pstate) {
     const size_t npx = (size_t)Hs * Ws;
     const int tw = (Ws + TG - 1) / TG, th = (Hs + TG - 1) / TG;
     const size_t nt = (size_t)tw * th;
     if (s.qcap == 0) s.qcap = npx / 8 > (1u << 20) ? npx / 8 : (1u << 20);
     if (s.qcap > npx + 1024) s.qcap = npx + 1024;
-    for (int v = 0; v < nviews; v++) {
-        int rc = 0;
-        rc |= s.st[v].ensure(npx);
-        rc |= s.tt[v].ensure(npx * 4);
-        rc |= s.pstate[v].ensure(npx * 4);
-        rc |= s.tile_u8[v].ensure(nt * 2);
-        rc |= s.tile_i32[v].ensure(nt * 4 * 11);
-        rc |= s.qkey[v].ensure(s.qcap * 8 * 3);
-        rc |= s.qidx[v].ensure(s.qcap * 4 * 3);
-        if (rc) return VSC_E_NOMEM;
-    }
-    return VSC_OK;
+    int rc = 0;
+    rc |= s.st[v].ensure(npx);
+    if (need_tt) rc |= s.tt[v].ensure(npx * 4);
+    if (need_pstate) rc |= s.pstate[v].ensure(npx * 4);
+    rc |= s.tile_u8[v].ensure(nt * 2);
+    rc |= s.tile_i32[v].ensure(nt * 4 * 11);
+    rc |= s.qkey[v].ensure(s.qcap * 8 * 3);
+    rc |= s.qidx[v].ensure(s.qcap * 4 * 3);
+    return rc ? VSC_E_NOMEM : VSC_OK;
 }
 struct ViewSpec {       // one eye of one frame for the hole-filling launch
     Slot* fr;           // the frame slot that owns the scratch buffers and the frame scalars
@@ -609,11 +607,15 @@ struct ViewSpec {       // one eye of one frame for the hole-filling launch
     uchar4* img;
     const unsigned* holes;   // hole bitmap written by the warp kernel (or pack_holes_kernel)
     int k0, k1;         // columns the back end reads
+    // Optional [Hs*Ws] 32-bit buffers lent for the arrival times T and the order words: buffers of the frame that are
+    // dead by the time the hole filling starts (null = the slot's own scratch).  Only written / read near holes.
+    float* tt = nullptr;
+    unsigned* pstate = nullptr;
 };
 // `s` is the group leader (stream, launch / profiling bookkeeping); the views may belong to several frame slots
 static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, int nviews) {
     if (nviews < 1 || nviews > TELEA_MAX_VIEWS) return fail(VSC_E_INVALID, "bad view count");
-    for (int v = 0; v < nviews; v++) { int rc = ensure_telea(*vs[v].fr, Hs, Ws, 2); if (rc) return rc; }
+    for (int v = 0; v < nviews; v++) { int rc = ensure_telea_view(*vs[v].fr, vs[v].b, Hs, Ws, !vs[v].tt, !vs[v].pstate); if (rc) return rc; }
     TeleaArgs a;
     memset(&a, 0, sizeof a);
     a.Hs = Hs; a.Ws = Ws; a.tw = (Ws + TG - 1) / TG; a.th = (Hs + TG - 1) / TG;
@@ -630,7 +632,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
         const int b = vs[v].b;
         TeleaView& V = a.v[v];
         V.img = vs[v].img; V.holes = vs[v].holes;
-        V.st = f.st[b].as<uint8_t>(); V.tt = f.tt[b].as<float>();
+        V.st = f.st[b].as<uint8_t>(); V.tt = vs[v].tt ? vs[v].tt : f.tt[b].as<float>();
         V.tile_cnt = f.tile_u8[b].as<unsigned char>(); V.tile_need = V.tile_cnt + nt;
         int* ib = f.tile_i32[b].as<int>();
         V.lab = ib; V.csize = ib + nt; V.ctiles = ib + 2 * nt; V.cneed = ib + 3 * nt; V.cslot = ib + 4 * nt;
@@ -638,7 +640,7 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
         V.cl_fill = ib + 9 * nt; V.tile_list = ib + 10 * nt;
         V.qkey[0] = f.qkey[b].as<unsigned long long>(); V.qkey[1] = V.qkey[0] + f.qcap; V.qkey[2] = V.qkey[1] + f.qcap;
         V.qidx[0] = f.qidx[b].as<unsigned>(); V.qidx[1] = V.qidx[0] + f.qcap; V.qidx[2] = V.qidx[1] + f.qcap;
-        V.pstate = f.pstate[b].as<unsigned>();
+        V.pstate = vs[v].pstate ? vs[v].pstate : f.pstate[b].as<unsigned>();
         V.qcap = (int)f.qcap;
         V.fs = f.scalars.as<FrameScalars>();
         V.vi = b;
@@ -754,6 +756,13 @@ static int enqueue_group(vsc_ctx* ctx, Slot* fr, int n, int dtype, const vsc_geo
         }
         vs[2 * i] = ViewSpec{&s, 0, cur[2 * i], vm[0], g.left_crop, g.left_crop + g.crop_w};
         vs[2 * i + 1] = ViewSpec{&s, 1, cur[2 * i + 1], vm[1], g.right_crop, g.right_crop + g.crop_w};
+        if (smoothing) {
+            // HBM capacity bounds the frames in flight (3.6 GB per 4K frame): the pre-bilateral views and the depth
+            // map are dead once the bilateral filter has run, so they serve as T (both eyes) and order words (left eye)
+            vs[2 * i].tt = s.viewA[0].as<float>();
+            vs[2 * i + 1].tt = s.viewA[1].as<float>();
+            vs[2 * i].pstate = s.depth_ss.as<unsigned>();
+        }
     }
     int rc = run_telea(ctx, lead, g.ss_h, g.ss_w, vs, 2 * n);
     if (rc) return rc;
