@@ -60,6 +60,24 @@ def test_in_order_publisher(tmp_path):
     assert not list(tmp_path.glob('*.ready')) and not list(tmp_path.glob('.*.part'))
 
 
+def test_sweep_parameter_grid():
+    """sbs_sweep.py: slider names / ranges of sbs_tester.py:356-362, cartesian product."""
+    sys.path.insert(0, PKG)
+    import sbs_sweep
+    assert sbs_sweep.parse_param('max_disparity=20:60:10') == ('max_disparity', [20.0, 30.0, 40.0, 50.0, 60.0])
+    assert sbs_sweep.parse_param('depth_gamma=0.2, 0.35,0.5') == ('depth_gamma', [0.2, 0.35, 0.5])
+    assert sbs_sweep.parse_param('super_sampling=1:4:1.5')[1] == [1.0, 2.5, 4.0]
+    for bad in ('gamma=1', 'max_disparity=1', 'convergence=60', 'sharpen=0:16:0', 'sharpen', 'edge_softness='):
+        with pytest.raises(ValueError):
+            sbs_sweep.parse_param(bad)
+    base = {k: 1.0 for k in sbs_sweep.SLIDERS}
+    g = sbs_sweep.grid(base, ['max_disparity=10,20', 'sharpen=0:16:8'])
+    assert len(g) == 6 and g[0]['max_disparity'] == 10.0 and g[0]['sharpen'] == 0.0 and g[5] == {**base, 'max_disparity': 20.0, 'sharpen': 16.0}
+    assert sbs_sweep.grid(base, []) == [base]
+    with pytest.raises(ValueError):
+        sbs_sweep.grid(base, ['sharpen=1', 'sharpen=2'])
+
+
 def test_raw_frame_sink_writes_in_clip_order(tmp_path):
     """frames arrive out of order from several workers, the stream is in clip order."""
     import threading
