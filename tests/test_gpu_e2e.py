@@ -80,6 +80,19 @@ def test_near_black_quirk(gen):
     assert np.array_equal(out0, O.process_frame(rgb, depth, O.Params(artifact_smoothing=0.0)))
 
 
+def test_near_black_quirk_many_rows(gen):
+    """Same quirk on a frame with more (row, segment) work items than the conditional re-run's grid holds, so its
+    CTAs stride over several items (and one eye only: the other eye's maximum is above 1.0)."""
+    h, w = 420, 700
+    rgb = np.ones((h, w, 3), np.uint8)
+    _, depth = make_pair(h, w, seed=5)
+    out = gen.process_frame(rgb, depth)
+    assert np.array_equal(out, O.process_frame(rgb, depth)) and (out >= 254).all()
+    rgb[:, :8] = 7                       # reaches only the left part of the views
+    out = gen.process_frame(rgb, depth)
+    assert np.array_equal(out, O.process_frame(rgb, depth))
+
+
 def test_flat_depth(gen):
     rgb, _ = make_pair(64, 96, seed=4)
     depth = np.full((64, 96), 77, np.uint8)
