@@ -602,8 +602,8 @@ __device__ __noinline__ void outer_lane_dataflow(const TeleaView& V, MarchShared
                     tn[q] = 1.0e6f; in_[q] = false;
                     if ((yy >= 0 && yy < Hs && xx >= 0 && xx < Ws)) {
                         const size_t p = (size_t)yy * Ws + xx;
-                        tn[q] = *(volatile float*)&V.tt[p];
-                        in_[q] = (*(volatile unsigned char*)&V.st[p] & O_MASK) == O_INSIDE;
+                        tn[q] = V.tt[p];       // ordered after the ring reads by the fence above (CTA scope: same SM, same L1)
+                        in_[q] = (V.st[p] & O_MASK) == O_INSIDE;
                     }
                 }
                 // the four corner solves in min4's pairing: (up,left) (down,left) | (up,right) (down,right)
