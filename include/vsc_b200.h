@@ -167,7 +167,9 @@ int vsc_slot_kernel_times(vsc_ctx *ctx, int slot, int max_n, const char **names,
  * event, end records once every slot stream has drained and returns the elapsed milliseconds */
 int vsc_timer_begin(vsc_ctx *ctx);
 int vsc_timer_end(vsc_ctx *ctx, float *ms);
-/* copies of slot 0's intermediates / Telea state after a completed call, for stage bisection in tests */
+/* copies of slot 0's intermediates after a completed call, for stage bisection (which: 0 rgb_st, 1 depth_st,
+ * 2 depth_ss, 3/4 pre-bilateral views, 5/6 filtered views, 7/8 hole bitmaps).  With artifact_smoothing > 0 the hole
+ * filling reuses buffers 2, 3 and 4 as scratch, so they no longer hold the intermediate afterwards. */
 int vsc_debug_fetch(vsc_ctx *ctx, int which, void *dst, size_t bytes);
 int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, size_t n);
 /* 64 phase counters of the hole-filling march (non-zero only in -DVSC_TELEA_STATS profiling builds) */
