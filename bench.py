@@ -366,7 +366,7 @@ def main():
     ap.add_argument('--batch', type=int, default=300, help='frames per step per GPU (BASELINE.json configs[1]: a 300-frame clip)')
     ap.add_argument('--slots', type=int, default=30, help='slots (CUDA streams) per GPU')
     ap.add_argument('--group', type=int, default=4, help='frames per slot submission (share a stream and one hole-filling launch)')
-    ap.add_argument('--cpu-frames', type=int, default=2)
+    ap.add_argument('--cpu-frames', type=int, default=4, help='frames of the bounded CPU-baseline sample (about 3 s each on 16 threads)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
