@@ -86,6 +86,26 @@ def test_gamma_within_one_ulp_of_torch(g):
     assert (mine != exact).mean() < 1e-3          # the oracle's pow is correctly rounded almost everywhere
 
 
+def test_pow_specification_tables_and_accuracy():
+    """The deterministic pow (float order): its tables are what the specification says and the result is the
+    correctly rounded power for every sampled input (the CUDA path is compared with this oracle bit for bit)."""
+    import ctypes as C
+    invc, log2c, exp2t = (C.c_double * 128)(), (C.c_double * 128)(), (C.c_double * 64)()
+    O.lib().orc_pow_tables(invc, log2c, exp2t)
+    c = 1.0 + (np.arange(128) + 0.5) / 128.0
+    assert np.array_equal(np.array(invc), 1.0 / c)                               # IEEE division: exact agreement
+    assert np.abs(np.array(log2c) - np.log2(c)).max() < 4e-16
+    assert np.abs(np.array(exp2t) - np.exp2(np.arange(64) / 64.0)).max() < 4e-16 and exp2t[0] == 1.0
+    rng = np.random.default_rng(7)
+    x = np.clip(rng.random(400000, dtype=np.float32), np.float32(0.001), 1)
+    x[:4] = [0.001, 1.0, 0.5, np.nextafter(np.float32(1), np.float32(0))]
+    for g in (0.1, 0.2, 0.35, 0.9, 1.7, 2.5):
+        exact = np.power(x.astype(np.float64), float(np.float32(g))).astype(np.float32)
+        assert np.array_equal(O.apply_gamma(x, g), exact), g
+    # ATen's special cases are float products (pow_tensor_scalar_optimized_kernel), not correctly rounded powers
+    assert np.array_equal(O.apply_gamma(x, 2.0), x * x) and np.array_equal(O.apply_gamma(x, 3.0), (x * x) * x)
+
+
 def _warp_literal_torch(image, depth, md, sign):
     """forward_warp_stereo's algorithm, stated literally: ascending-depth argsort, floor scatters, then
     ceil scatters of the frac > 0.3 subset, last writer wins."""
