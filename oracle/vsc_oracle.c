@@ -753,6 +753,143 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Two-pass restatement of the same algorithm (design check for the GPU march, DESIGN.md 6 "next"):
+ * the arrival times T and the ORDER in which hole pixels are computed depend on the mask alone, so
+ *   pass A runs the fast march without colours and records ord[p] (0,1,2,... in computation order);
+ *   pass B visits the hole pixels in that order and applies the Telea formula, where "pixel q is still
+ *   INSIDE at the time p is computed" is simply ord[q] >= ord[p] - no flags, no queue.
+ * Must give exactly orc_telea_u8c3's result (tests/test_oracle_vs_libs.py).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_telea_u8c3_two_pass(uint8_t *img, const uint8_t *mask, int H, int W, int radius) {
+    const int R = H + 2, C = W + 2;
+    int range = radius < 1 ? 1 : (radius > 100 ? 100 : radius);
+    size_t N = (size_t)R * C;
+    uint8_t *f = calloc(N, 1), *band = calloc(N, 1), *o = calloc(N, 1);
+    float *t = malloc(N * sizeof(float));
+    int32_t *ord = malloc(N * sizeof(int32_t));      /* -1: never a hole; INT32_MAX: hole not computed */
+    uint32_t *seq = NULL;
+    size_t nseq = 0, nmask = 0;
+    for (size_t k = 0; k < N; k++) { t[k] = 1.0e6f; ord[k] = -1; }
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            if (mask[(size_t)y * W + x]) { size_t p = (size_t)(y + 1) * C + x + 1; f[p] = T_INSIDE; ord[p] = INT32_MAX; nmask++; }
+    if (nmask == 0) goto done2;
+    seq = malloc(nmask * sizeof(uint32_t));
+    for (int i = 1; i < R - 1; i++)
+        for (int j = 1; j < C - 1; j++) {
+            size_t p = (size_t)i * C + j;
+            if (f[p]) continue;
+            if (f[p - C] || f[p + C] || f[p - 1] || f[p + 1]) band[p] = T_INSIDE;
+        }
+    pq_t heap = {0}, outq = {0};
+    for (int i = 1; i < R - 1; i++)
+        for (int j = 1; j < C - 1; j++)
+            if (band[(size_t)i * C + j]) { pq_push(&heap, i, j, 0.f); pq_push(&outq, i, j, 0.f); t[(size_t)i * C + j] = 0.f; }
+    for (int i = 1; i < R - 1; i++)
+        for (int j = 1; j < C - 1; j++) {
+            size_t p = (size_t)i * C + j;
+            if (f[p] || band[p]) continue;
+            int hit = 0;
+            for (int di = -range; di <= range && !hit; di++) {
+                int ii = i + di; if (ii < 0 || ii >= R) continue;
+                for (int dj = -range; dj <= range; dj++) {
+                    int jj = j + dj; if (jj < 0 || jj >= C) continue;
+                    if (f[(size_t)ii * C + jj]) { hit = 1; break; }
+                }
+            }
+            if (hit) o[p] = T_INSIDE;
+        }
+    {   /* outer ring distances, as in orc_telea_u8c3 */
+        int ii, jj;
+        while (pq_pop(&outq, &ii, &jj)) {
+            o[(size_t)ii * C + jj] = T_CHANGE;
+            for (int q = 0; q < 4; q++) {
+                int i = ii + (q == 0 ? -1 : (q == 2 ? 1 : 0)), j = jj + (q == 1 ? -1 : (q == 3 ? 1 : 0));
+                if (i <= 0 || j <= 0 || i >= R - 1 || j >= C - 1) continue;
+                if (o[(size_t)i * C + j] == T_INSIDE) {
+                    float dist = fmm_min4(i, j, o, t, C);
+                    t[(size_t)i * C + j] = dist; o[(size_t)i * C + j] = T_BAND;
+                    pq_push(&outq, i, j, dist);
+                }
+            }
+        }
+        for (size_t k = 0; k < N; k++)
+            if (o[k] == T_CHANGE) { o[k] = T_KNOWN; t[k] = -t[k]; }
+    }
+    {   /* pass A: the inpainting march WITHOUT colours - arrival times and computation order only */
+        int ii, jj;
+        while (pq_pop(&heap, &ii, &jj)) {
+            f[(size_t)ii * C + jj] = T_KNOWN;
+            for (int q = 0; q < 4; q++) {
+                int i = ii + (q == 0 ? -1 : (q == 2 ? 1 : 0)), j = jj + (q == 1 ? -1 : (q == 3 ? 1 : 0));
+                if (i <= 0 || j <= 0 || i >= R - 1 || j >= C - 1) continue;
+                size_t p = (size_t)i * C + j;
+                if (f[p] != T_INSIDE) continue;
+                float dist = fmm_min4(i, j, f, t, C);
+                t[p] = dist;
+                ord[p] = (int32_t)nseq; seq[nseq++] = (uint32_t)p;
+                f[p] = T_BAND;
+                pq_push(&heap, i, j, dist);
+            }
+        }
+    }
+    /* pass B: colours in the recorded order; INSIDE(q) at step k  <=>  ord[q] >= k */
+    for (size_t k = 0; k < nseq; k++) {
+        const size_t p = seq[k];
+        const int i = (int)(p / C), j = (int)(p % C);
+        const int32_t kk = (int32_t)k;
+#define INS(q) (ord[q] >= kk)
+        float gtx, gty;
+        if (!INS(p + 1)) { if (!INS(p - 1)) gtx = (t[p + 1] - t[p - 1]) * 0.5f; else gtx = t[p + 1] - t[p]; }
+        else { if (!INS(p - 1)) gtx = t[p] - t[p - 1]; else gtx = 0.f; }
+        if (!INS(p + C)) { if (!INS(p - C)) gty = (t[p + C] - t[p - C]) * 0.5f; else gty = t[p + C] - t[p]; }
+        else { if (!INS(p - C)) gty = t[p] - t[p - C]; else gty = 0.f; }
+        float Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Ia[3] = {0, 0, 0};
+        float s[3] = {1.0e-20f, 1.0e-20f, 1.0e-20f};
+        for (int kr = i - range; kr <= i + range; kr++) {
+            int km = kr - 1 + (kr == 1), kp = kr - 1 - (kr == R - 2);
+            for (int l = j - range; l <= j + range; l++) {
+                int lm = l - 1 + (l == 1), lp = l - 1 - (l == C - 2);
+                if (!(kr > 0 && l > 0 && kr < R - 1 && l < C - 1)) continue;
+                size_t pk = (size_t)kr * C + l;
+                if (INS(pk)) continue;
+                if ((l - j) * (l - j) + (kr - i) * (kr - i) > range * range) continue;
+                float ry = (float)(i - kr), rx = (float)(j - l);
+                float vl = rx * rx + ry * ry;
+                float dst = (float)(1. / ((double)vl * sqrt((double)vl)));
+                float lev = (float)(1. / (1 + fabs((double)(t[pk] - t[p]))));
+                float dir = rx * gtx + ry * gty;
+                if (fabs((double)dir) <= 0.01) dir = 0.000001f;
+                float w = fabsf(dst * lev * dir);
+                int fr = !INS(pk + 1), fl = !INS(pk - 1), fd = !INS(pk + C), fu = !INS(pk - C);
+                for (int c = 0; c < 3; c++) {
+#define PIX(yy, xx) ((int)img[((size_t)(yy) * W + (xx)) * 3 + c])
+                    float gix, giy;
+                    if (fr) { if (fl) gix = (float)(PIX(km, lp + 1) - PIX(km, lm - 1)) * 2.0f; else gix = (float)(PIX(km, lp + 1) - PIX(km, lm)); }
+                    else { if (fl) gix = (float)(PIX(km, lp) - PIX(km, lm - 1)); else gix = 0.f; }
+                    if (fd) { if (fu) giy = (float)(PIX(kp + 1, lm) - PIX(km - 1, lm)) * 2.0f; else giy = (float)(PIX(kp + 1, lm) - PIX(km, lm)); }
+                    else { if (fu) giy = (float)(PIX(kp, lm) - PIX(km - 1, lm)); else giy = 0.f; }
+                    Ia[c] += w * (float)PIX(kr - 1, l - 1);
+                    Jx[c] -= w * (gix * rx);
+                    Jy[c] -= w * (giy * ry);
+                    s[c] += w;
+#undef PIX
+                }
+            }
+        }
+        for (int c = 0; c < 3; c++) {
+            float sat = (float)(Ia[c] / s[c] + (Jx[c] + Jy[c]) / (sqrt(Jx[c] * Jx[c] + Jy[c] * Jy[c]) + 1.0e-20f) + 0.5f);
+            long r = lrintf(sat);
+            img[((size_t)(i - 1) * W + (j - 1)) * 3 + c] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+#undef INS
+    }
+    free(heap.a); free(outq.a);
+done2:
+    free(f); free(band); free(o); free(t); free(ord); free(seq);
+}
+
+/* ------------------------------------------------------------------------------------------
  * _sharpen_image (stereo_core.py:414-434): blur = gauss(5x5, sigma 1, reflect);
  * out = clamp(img + s*(img - blur), 0, 255) with unfused sub, mul, add.  planar [C,H,W].
  * ---------------------------------------------------------------------------------------- */

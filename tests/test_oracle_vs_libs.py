@@ -184,6 +184,30 @@ def test_telea_bit_exact_vs_cv2():
         assert np.array_equal(O.dilate3(mask), cv2.dilate(mask, np.ones((3, 3), np.uint8)))
 
 
+def test_telea_order_then_colour_decomposition():
+    """Arrival times and the computation order of hole pixels depend on the mask alone; computing the colours
+    afterwards in that order ('still unknown' = later in the order) reproduces the one-pass algorithm exactly.
+    This is the property the next step of the GPU march relies on."""
+    rng = np.random.default_rng(21)
+    for h, w, kind in [(60, 90, 'speckle'), (80, 70, 'dense'), (50, 120, 'cracks'), (64, 64, 'blob'), (40, 40, 'full-rows')]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if kind == 'speckle':
+            m = rng.random((h, w)) < 0.03
+        elif kind == 'dense':
+            m = rng.random((h, w)) < 0.35
+        elif kind == 'cracks':
+            m = np.zeros((h, w), bool); m[:, 20] = True; m[25, :] = True; m[5:45, 60:63] = True
+        elif kind == 'blob':
+            yy, xx = np.mgrid[:h, :w]; m = (yy - 30) ** 2 + (xx - 34) ** 2 < 15 ** 2
+        else:
+            m = np.zeros((h, w), bool); m[10:14] = True; m[:, :2] = True
+        mask = m.astype(np.uint8) * 255
+        one = O.telea(img, mask, 3)
+        two = O.telea_two_pass(img, mask, 3)
+        assert np.array_equal(one, two), kind
+        assert np.array_equal(one, cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)), kind
+
+
 def test_telea_known_answers():
     """const-101 image with a 1-px hole inpaints to 102 (+0.5 and round both apply), const-100 to 100."""
     for val, want in ((101, 102), (100, 100)):
