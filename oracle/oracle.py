@@ -232,14 +232,15 @@ def telea(img: np.ndarray, mask: np.ndarray, radius: int = 3, return_t: bool = F
     return (img, t) if return_t else img
 
 
-def telea_two_pass(img: np.ndarray, mask: np.ndarray, radius: int = 3) -> np.ndarray:
+def telea_two_pass(img: np.ndarray, mask: np.ndarray, radius: int = 3, return_order: bool = False):
     """Same result as telea(), computed as 'arrival times + order from the mask alone, then colours in that order'
     (orc_telea_u8c3_two_pass: the decomposition the GPU march is heading for)."""
     img = np.ascontiguousarray(img, np.uint8).copy()
     mask = np.ascontiguousarray(mask, np.uint8)
     h, w, _ = img.shape
-    lib().orc_telea_u8c3_two_pass(_p(img), _p(mask), h, w, radius)
-    return img
+    order = np.empty((h + 2, w + 2), np.int32) if return_order else None
+    lib().orc_telea_u8c3_two_pass(_p(img), _p(mask), h, w, radius, _p(order) if return_order else None)
+    return (img, order[1:-1, 1:-1]) if return_order else img
 
 
 def sharpen(x: np.ndarray, strength: float) -> np.ndarray:

@@ -760,7 +760,8 @@ done:
  *   INSIDE at the time p is computed" is simply ord[q] >= ord[p] - no flags, no queue.
  * Must give exactly orc_telea_u8c3's result (tests/test_oracle_vs_libs.py).
  * ---------------------------------------------------------------------------------------- */
-ORC_API void orc_telea_u8c3_two_pass(uint8_t *img, const uint8_t *mask, int H, int W, int radius) {
+/* ord_out: optional [(H+2)*(W+2)] computation order of the hole pixels (-1 elsewhere), for analysis */
+ORC_API void orc_telea_u8c3_two_pass(uint8_t *img, const uint8_t *mask, int H, int W, int radius, int32_t *ord_out) {
     const int R = H + 2, C = W + 2;
     int range = radius < 1 ? 1 : (radius > 100 ? 100 : radius);
     size_t N = (size_t)R * C;
@@ -886,6 +887,7 @@ ORC_API void orc_telea_u8c3_two_pass(uint8_t *img, const uint8_t *mask, int H, i
     }
     free(heap.a); free(outq.a);
 done2:
+    if (ord_out) memcpy(ord_out, ord, N * sizeof(int32_t));
     free(f); free(band); free(o); free(t); free(ord); free(seq);
 }
 
