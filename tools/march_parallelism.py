@@ -30,6 +30,15 @@ for side in ('left', 'right'):
         win_o = ordp[y:y + 9, x:x + 9]; win_l = level[y:y + 9, x:x + 9]
         m = (win_o >= 0) & (win_o < k)
         level[y + 4, x + 4] = 1 + (win_l[m].max() if m.any() else 0)
+    # per cluster (holes linked within 15 px, the GPU's tile clustering to a good approximation): size, depth
+    from scipy import ndimage
+    lab, ncl = ndimage.label(cv2.dilate(mask, np.ones((15, 15), np.uint8)) > 0, structure=np.ones((3, 3)))
+    cl = lab[ys, xs]
+    lv = level[ys + 4, xs + 4]
+    sizes = np.bincount(cl, minlength=ncl + 1); depths = np.zeros(ncl + 1, np.int64)
+    np.maximum.at(depths, cl, lv)
+    top = np.argsort(-sizes)[:5]
+    print(f'{side}: {ncl} clusters; largest: ' + ', '.join(f'{sizes[c]} px / depth {depths[c]} (x{sizes[c] / max(depths[c], 1):.0f})' for c in top if sizes[c]))
     n, depth_ = len(ys), int(level.max())
     print(f'{side}: {n} hole pixels, dependency depth {depth_}, average parallelism {n / max(depth_, 1):.1f} '
           f'(analysis {time.time() - t0:.1f} s, {rows} rows)')
