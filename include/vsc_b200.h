@@ -171,7 +171,9 @@ int vsc_timer_end(vsc_ctx *ctx, float *ms);
  * 2 depth_ss, 3/4 pre-bilateral views, 5/6 filtered views, 7/8 hole bitmaps).  With artifact_smoothing > 0 the hole
  * filling reuses buffers 2, 3 and 4 as scratch, so they no longer hold the intermediate afterwards. */
 int vsc_debug_fetch(vsc_ctx *ctx, int which, void *dst, size_t bytes);
-int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, size_t n);
+/* after vsc_stage_inpaint: arrival times, state bytes and order words (index of every computed hole pixel in the
+ * reference's computation order) of slot 0; any pointer may be null */
+int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, uint32_t *ord, size_t n);
 /* 64 phase counters of the hole-filling march (non-zero only in -DVSC_TELEA_STATS profiling builds) */
 int vsc_debug_telea_stats(vsc_ctx *ctx, unsigned long long *out64);
 /* test hook: set the hole-filling queue capacity (entries per view) to exercise the overflow/re-run path */

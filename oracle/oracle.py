@@ -26,7 +26,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_LIB_PATH) or \
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, 'vsc_oracle.c')):
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ('vsc_oracle.c', 'march_model.c')):
         subprocess.check_call(['make', '-C', _HERE, '-s', '-B'])
     return _LIB_PATH
 
@@ -241,6 +241,23 @@ def telea_two_pass(img: np.ndarray, mask: np.ndarray, radius: int = 3, return_or
     order = np.empty((h + 2, w + 2), np.int32) if return_order else None
     lib().orc_telea_u8c3_two_pass(_p(img), _p(mask), h, w, radius, _p(order) if return_order else None)
     return (img, order[1:-1, 1:-1]) if return_order else img
+
+
+MARCH_STATS = ('generations', 'tasks', 'largest_bucket', 'sweeps', 'max_sweeps', 'sorted_buckets', 'max_distinct_t',
+               'evaluations')
+
+
+def march_model(mask: np.ndarray, radius: int = 3):
+    """The GPU march's bulk-synchronous schedule, run sequentially (march_model.c): arrival times [h+2,w+2] (as
+    telea(return_t=True)), computation order [h,w] (as telea_two_pass(return_order=True)) and the shape of the work
+    for the outer-ring pass and the inpainting pass."""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    h, w = mask.shape
+    t = np.empty((h + 2, w + 2), np.float32)
+    order = np.empty((h + 2, w + 2), np.int32)
+    stats = np.zeros((2, len(MARCH_STATS)), np.int64)
+    lib().orc_march_model(_p(mask), h, w, radius, _p(t), _p(order), _p(stats))
+    return t, order[1:-1, 1:-1], [dict(zip(MARCH_STATS, map(int, row))) for row in stats]
 
 
 def sharpen(x: np.ndarray, strength: float) -> np.ndarray:

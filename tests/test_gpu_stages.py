@@ -194,6 +194,47 @@ def test_inpaint_bit_exact(ctx, name):
     assert np.array_equal(out, ref), f'{(out != ref).any(axis=2).sum()} px differ'
 
 
+def _march_state(ctx, h, w):
+    """arrival times, state bytes and order words of the last vsc_stage_inpaint call"""
+    tt = np.empty((h, w), np.float32); st = np.empty((h, w), np.uint8); od = np.empty((h, w), np.uint32)
+    _lib.check(_lib.load().vsc_debug_telea_state(ctx.handle, 0, _lib.ptr(tt), _lib.ptr(st), _lib.ptr(od), h * w))
+    return tt, st, od
+
+
+@pytest.mark.parametrize('name', ['1px', 'vcrack', 'blobs', 'left_band', 'corners', 'disc', 'dense', 'diag'])
+def test_march_times_and_order_match_the_sequential_march(ctx, name):
+    """Stage A of the march on its own: every arrival time T (holes, band, outer ring) equals the one-pop-at-a-time
+    oracle bit for bit, and inside every cluster the hole pixels are computed in the oracle's order."""
+    from scipy import ndimage
+    h, w = 120, 170
+    img = make_rgb(h, w, seed=2)
+    hole = _masks(h, w)[name]
+    valid = (~hole).astype(np.uint8)
+    img[hole] = 0
+    _inpaint_case(ctx, img, valid)
+    tt, st, od = _march_state(ctx, h, w)
+    mask = O.dilate3(((1 - valid.astype(np.float32)) * 255).astype(np.uint8))
+    t_ref, ord_ref, _ = O.march_model(mask)
+    _, t_seq = O.telea(img, mask, 3, return_t=True)
+    assert np.array_equal(t_ref.view(np.uint32), t_seq.view(np.uint32))       # the model is the sequential march
+    near = st != 0                                                             # hole, band or ring
+    assert np.array_equal(near & (mask > 0), mask > 0)
+    bad_t = near & (tt.view(np.uint32) != t_ref[1:-1, 1:-1].view(np.uint32))
+    assert not bad_t.any(), f'{bad_t.sum()} arrival times differ, first at {np.argwhere(bad_t)[0]}'
+    # clusters as the library forms them: 8x8 tiles that hold a hole / band / ring pixel, 8-connected
+    th, tw = (h + 7) // 8, (w + 7) // 8
+    occ = np.zeros((th * 8, tw * 8), bool); occ[:h, :w] = near
+    lab, ncl = ndimage.label(occ.reshape(th, 8, tw, 8).any(axis=(1, 3)), structure=np.ones((3, 3)))
+    lab_px = np.repeat(np.repeat(lab, 8, 0), 8, 1)[:h, :w]
+    for c in range(1, ncl + 1):
+        sel = (lab_px == c) & (mask > 0)
+        if not sel.any():
+            continue
+        got, ref = od[sel].astype(np.int64), ord_ref[sel].astype(np.int64)
+        assert len(np.unique(got)) == len(got)
+        assert np.array_equal(np.argsort(got), np.argsort(ref)), f'cluster {c}: computation order differs'
+
+
 def test_inpaint_const_image(ctx):
     """Constant image: the ill-conditioned unit-gradient term makes every ulp count."""
     img = np.full((20, 20, 3), 101, np.uint8)

@@ -208,6 +208,33 @@ def test_telea_order_then_colour_decomposition():
         assert np.array_equal(one, cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)), kind
 
 
+def test_march_model_equals_the_sequential_march():
+    """The GPU march's schedule (T buckets of 0.7, stable sort by T, first-popped-neighbour ownership, prefix-sum task
+    order, distances by fixed-point sweeps; march_model.c) gives the arrival times and the computation order of the
+    one-pop-at-a-time algorithm, bit for bit, and needs few sweeps."""
+    rng = np.random.default_rng(5)
+    masks = []
+    m = np.zeros((150, 200), np.uint8)
+    for _ in range(20):
+        cv2.circle(m, (int(rng.integers(0, 200)), int(rng.integers(0, 150))), int(rng.integers(1, 22)), 255, -1)
+    masks.append(m)
+    masks.append(cv2.dilate((rng.random((90, 120)) < 0.08).astype(np.uint8) * 255, np.ones((3, 3), np.uint8)))
+    m = np.zeros((200, 150), np.uint8); m[:, 50:53] = 255; m[10:180, 90:130] = 255; m[100:103, :] = 255; m[:, :9] = 255
+    masks.append(m)
+    m = np.zeros((160, 160), np.uint8)
+    cv2.line(m, (5, 5), (150, 110), 255, 3); cv2.line(m, (5, 155), (155, 20), 255, 7); cv2.ellipse(m, (80, 80), (60, 30), 30, 0, 360, 255, 5)
+    masks.append(m)
+    for mask in masks:
+        img = rng.integers(0, 256, mask.shape + (3,), dtype=np.uint8)
+        _, t = O.telea(img, mask, 3, return_t=True)
+        _, order = O.telea_two_pass(img, mask, 3, return_order=True)
+        t2, order2, stats = O.march_model(mask)
+        assert np.array_equal(t.view(np.uint32), t2.view(np.uint32))
+        assert np.array_equal(order, order2)
+        assert all(s['generations'] > 0 and s['max_sweeps'] <= 8 for s in stats), stats
+        assert stats[1]['tasks'] == int((mask > 0).sum())
+
+
 def test_telea_known_answers():
     """const-101 image with a 1-px hole inpaints to 102 (+0.5 and round both apply), const-100 to 100."""
     for val, want in ((101, 102), (100, 100)):

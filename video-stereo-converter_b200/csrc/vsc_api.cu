@@ -18,7 +18,7 @@
 #include <vector>
 
 #include "../../include/vsc_b200.h"
-#include "vsc_telea.cuh"
+#include "vsc_march.cuh"
 
 using namespace vsc;
 
@@ -349,6 +349,8 @@ static int set_smem_attrs() {
     CU(cudaFuncSetAttribute(backend_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(backend_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(telea_march_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSh<16>)));
+    CU(cudaFuncSetAttribute(telea_march_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSh<32>)));
     return VSC_OK;
 }
 
@@ -667,6 +669,16 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
     // persistent CTAs pulling clusters from a per-view queue (big clusters first); view-major launch order, so the
     // first CTAs to start take each view's biggest cluster
     dim3 cgrid(nviews, ctx->sm_count / 2);
+    static const int march_impl = getenv("VSC_MARCH_OLD") ? 0 : 1;      // A/B switch while the generation march is new
+    if (march_impl) {
+        prof_begin(s, "telea_march_kernel");
+        if (ctx->slots.size() == (size_t)ctx->group_size)     // one slot: nothing overlaps the march, favour its latency
+            telea_march_kernel<32><<<cgrid, 32 * 32, sizeof(MarchSh<32>), s.stream>>>(a);
+        else
+            telea_march_kernel<16><<<cgrid, 16 * 32, sizeof(MarchSh<16>), s.stream>>>(a);
+        KCHECK(s);
+        return VSC_OK;
+    }
     prof_begin(s, "telea_cluster_kernel");
     if (ctx->slots.size() == (size_t)ctx->group_size)     // one slot: nothing overlaps the march, favour its latency
         telea_cluster_kernel<TELEA_WARPS_LATENCY><<<cgrid, TELEA_WARPS_LATENCY * 32, 0, s.stream>>>(a);
@@ -1164,13 +1176,14 @@ extern "C" int vsc_stage_warp_f32(vsc_ctx* ctx, const float* image, const float*
 }
 
 // debug: copy the Telea state of slot 0 (after vsc_stage_inpaint) to the host
-extern "C" int vsc_debug_telea_state(vsc_ctx* ctx, int view, float* tt, uint8_t* st, size_t n) {
+extern "C" int vsc_debug_telea_state(vsc_ctx* ctx, int view, float* tt, uint8_t* st, uint32_t* ord, size_t n) {
     if (!ctx) return fail(VSC_E_INVALID, "null context");
     Slot& s = ctx->slots[0];
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
     if (tt) CU(cudaMemcpy(tt, s.tt[view].p, n * 4, cudaMemcpyDeviceToHost));
     if (st) CU(cudaMemcpy(st, s.st[view].p, n, cudaMemcpyDeviceToHost));
+    if (ord) CU(cudaMemcpy(ord, s.pstate[view].p, n * 4, cudaMemcpyDeviceToHost));
     return VSC_OK;
 }
 

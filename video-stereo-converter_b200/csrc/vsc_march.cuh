@@ -1,0 +1,556 @@
+// vsc_march.cuh — the march of the exact GPU Telea (cv2.inpaint(..., 3, INPAINT_TELEA),
+// /root/reference/helper/stereo_core.py:457; OpenCV photo/inpaint.cpp), one CTA per cluster of holes
+// (clusters: vsc_telea.cuh).  The reference pops a sorted list one pixel at a time and re-reads pixels it has just
+// written; here the same result is produced in two stages:
+//
+//   A. ORDER.  The arrival times T and the order in which hole pixels are computed depend on the mask alone.  Both
+//      fast-marching sweeps (outer distance ring, then the holes) run as bulk-synchronous GENERATIONS:
+//        bucket g   = queue entries with floor(T / 0.7) == g.  A pixel computed while bucket g is popped has
+//                     T in [popped T + 1/sqrt(2), popped T + 1], i.e. it belongs to bucket g+1 or g+2: three rotating
+//                     lists replace the sorted list and bucket g is complete before it is popped
+//        pop order  = (T, push order): lists are appended in push order, so a STABLE radix sort by T alone is exact
+//        ownership  = a pixel is computed by its FIRST popped 4-neighbour: atomicMin of (pop rank * 4 + q)
+//        task order = (owner's pop rank, q) = the sequential computation / push order; a prefix sum numbers the tasks J
+//        distances  = task J sees a neighbour as known iff it is outside the domain, older than this generation, or a
+//                     task J' < J of it.  Only the T of those same-generation neighbours is unknown up front; every
+//                     thread re-evaluates its tasks until nothing changes - the fixed point is unique because the
+//                     dependencies follow J (measured: <= 7 sweeps; the test suite pins this schedule with a sequential CPU model)
+//      No queue, no per-pixel waiting: a generation is a handful of data-parallel phases.
+//   B. COLOURS.  The hole pixels are inpainted in the recorded order as ONE dataflow without generations or CTA
+//      barriers: "pixel q was known when pixel J was computed" is ord[q] < J.  A warp takes the next pixel, stages its
+//      9x9 window and computes the 28 weights BEFORE it waits (they do not depend on colours), then waits only for the
+//      earlier hole pixels inside the window that are still in flight.  Finished pixels publish (index, colour) as one
+//      64-bit word in a shared-memory ring, so the dependent chain of a crack runs through shared memory: poll,
+//      9 sums in the reference's raster order, division / square root, publish.
+#pragma once
+#include "vsc_telea.cuh"
+
+namespace vsc {
+
+constexpr int MARCH_RING = 2048;                       // entries of the completion / colour ring (power of two)
+constexpr float MARCH_BUCKET_INV = 1.4285714285714286f; // 1 / 0.7 (bucket width < 1/sqrt(2), see header)
+constexpr unsigned MARCH_WATCHDOG = 1u << 24;          // polls before a wait gives up and reports an error (seconds)
+
+struct MarchWin {            // per-warp 9x9 window around the pixel being inpainted
+    unsigned img[81];
+    float tt[81];
+    unsigned char kn[84];    // 1 = known when this pixel is computed (outside the image: the KNOWN frame)
+    float taps[28 * 10];
+};
+
+template <int NW> struct MarchSh {
+    union {
+        unsigned hist[NW][256];                  // stage A: per-warp radix histograms
+        unsigned long long ring[MARCH_RING];     // stage B: (colour << 32) | (J + 1) once pixel J is final
+    } u;
+    unsigned tot[256];
+    int wsum[32];
+    int cnt[3];
+    int need_left, ci, nband, next_task, flag;
+    unsigned kmin, kmax, done_prefix;
+    TapTable tp;
+    MarchWin win[NW];
+};
+
+struct MarchScratch {        // the cluster's slices of the per-view scratch arrays
+    unsigned* band;          // initial band in raster order (generation 0 of both sweeps)
+    unsigned* L[3];          // rotating bucket lists
+    unsigned* sa;            // sort partner of the current list
+    unsigned* ka; unsigned* kb;   // sort keys (ping-pong); ka doubles as the ownership masks of a generation
+    unsigned* seq;           // tasks in computation order (stage B walks the hole sweep's copy)
+};
+
+template <int NW> __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const int s = wsum[w]; if (w < wid) woff += s; tot += s; }
+    total = tot;
+    __syncthreads();
+    return woff + inc - v;
+}
+
+// One stable counting pass of an LSD radix sort on bits [shift, shift+8) of (key - kmin).  A warp owns a contiguous
+// segment of the input, so equal digits keep their order without any cross-warp atomics.
+template <int NW>
+__device__ void radix_pass(const unsigned* ks, const unsigned* vs, unsigned* kd, unsigned* vd, int n, int shift, unsigned kmin, MarchSh<NW>& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < NW * 256; i += NW * 32) (&sh.u.hist[0][0])[i] = 0u;
+    __syncthreads();
+    const int seg = (((n + NW - 1) / NW) + 31) & ~31;
+    const int b0 = min(n, wid * seg), b1 = min(n, b0 + seg);
+    for (int base = b0; base < b1; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < b1;
+        const unsigned d = valid ? (((ks[i] - kmin) >> shift) & 255u) : (256u + (unsigned)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == __ffs(peers) - 1) sh.u.hist[wid][d] += (unsigned)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 256) {       // per digit: exclusive offsets over the warps, and the digit total
+        unsigned s = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { const unsigned t = sh.u.hist[w][tid]; sh.u.hist[w][tid] = s; s += t; }
+        sh.tot[tid] = s;
+    }
+    __syncthreads();
+    if (wid == 0) {        // exclusive scan of the 256 digit totals
+        unsigned loc[8], s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { loc[k] = sh.tot[lane * 8 + k]; s += loc[k]; }
+        unsigned inc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        unsigned ex = inc - s;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { sh.tot[lane * 8 + k] = ex; ex += loc[k]; }
+    }
+    __syncthreads();
+    for (int base = b0; base < b1; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < b1;
+        const unsigned key = valid ? ks[i] : 0u, val = valid ? vs[i] : 0u;
+        const unsigned d = valid ? (((key - kmin) >> shift) & 255u) : (256u + (unsigned)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid) {
+            const unsigned pos = sh.tot[d] + sh.u.hist[wid][d] + (unsigned)__popc(peers & ((1u << lane) - 1u));
+            kd[pos] = key; vd[pos] = val;
+        }
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) sh.u.hist[wid][d] += (unsigned)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+// sorts (k0,v0)[0,n) by the low nbits of (key - kmin); returns 0 if the result is in (k0,v0), 1 if in (k1,v1)
+template <int NW>
+__device__ int radix_sort(unsigned* k0, unsigned* v0, unsigned* k1, unsigned* v1, int n, int nbits, unsigned kmin, MarchSh<NW>& sh) {
+    int w = 0;
+    for (int shift = 0; shift < nbits; shift += 8) {
+        radix_pass<NW>(w ? k1 : k0, w ? v1 : v0, w ? k0 : k1, w ? v0 : v1, n, shift, kmin, sh);
+        w ^= 1;
+    }
+    return w;
+}
+
+// the reference's neighbour order: up, left, down, right
+__device__ __forceinline__ int nb_dy(int q) { return q == 0 ? -1 : (q == 2 ? 1 : 0); }
+__device__ __forceinline__ int nb_dx(int q) { return q == 1 ? -1 : (q == 3 ? 1 : 0); }
+
+// ---- stage A: one fast-marching sweep (OUTER: the distance ring around the holes; else the holes) ---------------
+// Returns the number of tasks; their pixels are sc.seq[0..), ord word (V.pstate) of a computed pixel = its index J.
+template <bool OUTER, int NW>
+__device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScratch& sc, int nband, int Hs, int Ws, int keep_x0, int keep_x1) {
+    const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31;
+    auto in_dom = [](unsigned char s) { return OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE); };
+    if (tid == 0) { sh.cnt[0] = 0; sh.cnt[1] = 0; sh.cnt[2] = 0; }
+    __syncthreads();
+    unsigned tbase = 0;
+    for (int g = 0; g < (1 << 20); g++) {
+        const int n = g == 0 ? nband : sh.cnt[g % 3];
+        if (n == 0) {
+            if (g == 0 || (sh.cnt[(g + 1) % 3] == 0 && sh.cnt[(g + 2) % 3] == 0)) break;
+            continue;
+        }
+        unsigned* cur = g == 0 ? sc.band : sc.L[g % 3];
+        const unsigned* S = cur;
+        if (g > 0) {      // pop order of the bucket: stable sort by T (generation 0 is the band in raster order, all T = 0)
+            if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+            __syncthreads();
+            unsigned kmn = 0xffffffffu, kmx = 0u;
+            for (int e = tid; e < n; e += nt) {
+                const unsigned k = __float_as_uint(V.tt[cur[e]]);       // T > 0: bit order = value order
+                sc.ka[e] = k; kmn = min(kmn, k); kmx = max(kmx, k);
+            }
+            kmn = __reduce_min_sync(0xffffffffu, kmn); kmx = __reduce_max_sync(0xffffffffu, kmx);
+            if (lane == 0) { atomicMin(&sh.kmin, kmn); atomicMax(&sh.kmax, kmx); }
+            __syncthreads();
+            const unsigned kmin = sh.kmin, span = sh.kmax - kmin;
+            const int nbits = span ? 32 - __clz(span) : 0;
+            if (radix_sort<NW>(sc.ka, cur, sc.kb, sc.sa, n, nbits, kmin, sh)) S = sc.sa;
+        }
+        // claims: the first popped neighbour (lowest pop rank, then lowest q) computes a pixel
+        for (int e = tid; e < n; e += nt) {
+            const unsigned p = S[e];
+            const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int yy = y + nb_dy(q), xx = x + nb_dx(q);
+                if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
+                const size_t nb = (size_t)yy * Ws + xx;
+                if (!in_dom(V.st[nb])) continue;
+                if (V.pstate[nb] >= 0x80000000u) atomicMin(&V.pstate[nb], 0x80000000u + (unsigned)(e * 4 + q));
+            }
+        }
+        __syncthreads();
+        // ownership (a thread takes a contiguous range of pops so that one prefix sum orders all tasks)
+        const int per = (n + nt - 1) / nt, e0 = min(n, tid * per), e1 = min(n, e0 + per);
+        int c = 0;
+        for (int e = e0; e < e1; e++) {
+            const unsigned p = S[e];
+            const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+            unsigned own = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int yy = y + nb_dy(q), xx = x + nb_dx(q);
+                if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
+                const size_t nb = (size_t)yy * Ws + xx;
+                if (!in_dom(V.st[nb])) continue;
+                if (__ldcg(&V.pstate[nb]) == 0x80000000u + (unsigned)(e * 4 + q)) own |= 1u << q;    // L2: sees the atomics
+            }
+            sc.ka[e] = own;
+            c += __popc(own);
+        }
+        int ntask;
+        const int off = block_excl_scan<NW>(c, sh.wsum, ntask);
+        unsigned* TL = sc.seq + tbase;
+        {
+            int j = off;
+            for (int e = e0; e < e1; e++) {
+                const unsigned own = sc.ka[e];
+                if (!own) continue;
+                const unsigned p = S[e];
+                const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (!(own & (1u << q))) continue;
+                    const unsigned nb = (unsigned)((y + nb_dy(q)) * Ws + (x + nb_dx(q)));
+                    TL[j] = nb;
+                    V.pstate[nb] = tbase + (unsigned)j;
+                    j++;
+                }
+            }
+        }
+        __syncthreads();
+        // distances: re-evaluate until the (unique) fixed point
+        while (true) {
+            int ch = 0;
+            for (int j = tid; j < ntask; j += nt) {
+                const unsigned p = TL[j], J = tbase + (unsigned)j;
+                const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+                float tn[4]; bool in_[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int yy = y + nb_dy(q), xx = x + nb_dx(q);
+                    tn[q] = 1.0e6f; in_[q] = false;           // outside the image: cv2's KNOWN frame with T = 1e6
+                    if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
+                        const size_t nb = (size_t)yy * Ws + xx;
+                        tn[q] = V.tt[nb];
+                        if (in_dom(V.st[nb])) in_[q] = V.pstate[nb] >= J;
+                    }
+                }
+                // min4's pairing: (up,left) (down,left) (up,right) (down,right)
+                const float s0 = fmm_solve(tn[0], tn[1], in_[0], in_[1]), s1 = fmm_solve(tn[2], tn[1], in_[2], in_[1]);
+                const float s2 = fmm_solve(tn[0], tn[3], in_[0], in_[3]), s3 = fmm_solve(tn[2], tn[3], in_[2], in_[3]);
+                const float d = fminf(fminf(s0, s1), fminf(s2, s3));
+                if (d != V.tt[p]) { V.tt[p] = d; ch = 1; }
+            }
+            if (!__syncthreads_or(ch)) break;
+        }
+        // push in task order: a stable split into the next two buckets
+        const int b1i = (g + 1) % 3, b2i = (g + 2) % 3;
+        const int tper = (ntask + nt - 1) / nt, j0 = min(ntask, tid * tper), j1 = min(ntask, j0 + tper);
+        int c1 = 0, inwin = 0;
+        for (int j = j0; j < j1; j++) {
+            const unsigned p = TL[j];
+            const int b = (int)floorf(__fmul_rn(V.tt[p], MARCH_BUCKET_INV));
+            if (b == g + 1) c1++;
+            else if (b != g + 2) sh.flag = 1;                   // cannot happen (header); reported as a scratch overflow
+            if (!OUTER) { const int x = (int)(p % (unsigned)Ws); inwin += (x >= keep_x0 && x < keep_x1) ? 1 : 0; }
+        }
+        int total1;
+        const int off1 = block_excl_scan<NW>(c1, sh.wsum, total1);
+        {
+            const int base1 = sh.cnt[b1i];
+            unsigned* L1 = sc.L[b1i] + base1;
+            unsigned* L2 = sc.L[b2i];
+            int p1 = off1, p2 = j0 - off1;
+            for (int j = j0; j < j1; j++) {
+                const unsigned p = TL[j];
+                const int b = (int)floorf(__fmul_rn(V.tt[p], MARCH_BUCKET_INV));
+                if (b == g + 1) L1[p1++] = p; else L2[p2++] = p;
+            }
+            if (!OUTER) {
+                inwin = __reduce_add_sync(0xffffffffu, inwin);
+                if (lane == 0 && inwin) atomicSub(&sh.need_left, inwin);
+            }
+            __syncthreads();
+            if (tid == 0) { sh.cnt[b1i] = base1 + total1; sh.cnt[b2i] = ntask - total1; sh.cnt[g % 3] = 0; }
+        }
+        tbase += (unsigned)ntask;
+        __syncthreads();
+        // Everything still queued is farther from the hole boundary than every pixel computed so far and cannot influence
+        // them; once all hole pixels inside the kept window are computed the rest of the cluster is never read.
+        if (!OUTER && sh.need_left <= 0) break;
+    }
+    return (int)tbase;
+}
+
+// ---- stage B: colours in the recorded order --------------------------------------------------------------------
+template <int NW>
+__device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned* seq, int ntask, int Hs, int Ws) {
+    const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
+    MarchWin& w = sh.win[wid];
+    for (int i = tid; i < MARCH_RING; i += nt) sh.u.ring[i] = 0ull;
+    if (tid == 0) { sh.next_task = 0; sh.done_prefix = 0u; }
+    __syncthreads();
+    constexpr unsigned NONE = 0xffffffffu;
+    while (true) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&sh.next_task, 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= ntask) break;
+        const unsigned p = seq[j];
+        const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+        // every pixel with index < D is final and visible; younger ones are looked up in the ring
+        const unsigned D = *(volatile unsigned*)&sh.done_prefix;
+        __threadfence_block();
+        unsigned pj[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int idx = lane + 32 * r;
+            pj[r] = NONE;
+            if (idx < 81) {
+                const int yy = y + idx / 9 - 4, xx = x + idx % 9 - 4;
+                unsigned c = 0; float t = 1.0e6f; unsigned char kn = 1;
+                if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
+                    const size_t q = (size_t)yy * Ws + xx;
+                    const unsigned char s = V.st[q];
+                    t = V.tt[q];
+                    c = *reinterpret_cast<const unsigned*>(&V.img[q]);
+                    if ((s & F_MASK) == F_INSIDE) {
+                        const unsigned o = V.pstate[q];
+                        kn = o < (unsigned)j;
+                        if (kn && o >= D) pj[r] = o;
+                    }
+                }
+                w.kn[idx] = kn; w.tt[idx] = t; w.img[idx] = c;
+            }
+        }
+        __syncwarp();
+#define MWI(yy, xx) (((yy) - y + 4) * 9 + ((xx) - x + 4))
+        // ---- everything that does not depend on colours: gradient of T, the 28 weights, which pixels each tap reads
+        const float dist = w.tt[MWI(y, x)];
+        float gtx, gty;
+        {
+            const bool r = w.kn[MWI(y, x + 1)], l = w.kn[MWI(y, x - 1)], d = w.kn[MWI(y + 1, x)], u = w.kn[MWI(y - 1, x)];
+            if (r) gtx = l ? __fmul_rn(__fsub_rn(w.tt[MWI(y, x + 1)], w.tt[MWI(y, x - 1)]), 0.5f) : __fsub_rn(w.tt[MWI(y, x + 1)], dist);
+            else gtx = l ? __fsub_rn(dist, w.tt[MWI(y, x - 1)]) : 0.f;
+            if (d) gty = u ? __fmul_rn(__fsub_rn(w.tt[MWI(y + 1, x)], w.tt[MWI(y - 1, x)]), 0.5f) : __fsub_rn(w.tt[MWI(y + 1, x)], dist);
+            else gty = u ? __fsub_rn(dist, w.tt[MWI(y - 1, x)]) : 0.f;
+        }
+        bool valid = false;
+        float wgt = 0.f, rx = 0.f, ry = 0.f;
+        int ic = 0, ixa = 0, ixb = 0, iya = 0, iyb = 0, mx = 0, my = 0;     // mx / my: 0 none, 1 one-sided, 2 central (x2)
+        if (lane < 28) {
+            const int dk = sh.tp.dk[lane], dl = sh.tp.dl[lane];
+            const int ky = y + dk, kx = x + dl;
+            if (ky >= 0 && ky < Hs && kx >= 0 && kx < Ws && w.kn[MWI(ky, kx)]) {
+                valid = true;
+                ry = (float)(-dk); rx = (float)(-dl);
+                const float lev = (float)__ddiv_rn(1.0, __dadd_rn(1.0, fabs((double)__fsub_rn(w.tt[MWI(ky, kx)], dist))));
+                float dir = __fadd_rn(__fmul_rn(rx, gtx), __fmul_rn(ry, gty));
+                if (fabs((double)dir) <= 0.01) dir = 0.000001f;
+                wgt = fabsf(__fmul_rn(__fmul_rn(sh.tp.dst[lane], lev), dir));
+                const bool fr = w.kn[MWI(ky, kx + 1)], fl = w.kn[MWI(ky, kx - 1)], fd = w.kn[MWI(ky + 1, kx)], fu = w.kn[MWI(ky - 1, kx)];
+                const int km = ky + (ky == 0), kp = ky - (ky == Hs - 1);
+                const int lm = kx + (kx == 0), lp = kx - (kx == Ws - 1);
+                ic = MWI(ky, kx);
+                if (fr) { mx = fl ? 2 : 1; ixa = MWI(km, lp + 1); ixb = fl ? MWI(km, lm - 1) : MWI(km, lm); }
+                else if (fl) { mx = 1; ixa = MWI(km, lp); ixb = MWI(km, lm - 1); }
+                if (fd) { my = fu ? 2 : 1; iya = MWI(kp + 1, lm); iyb = fu ? MWI(km - 1, lm) : MWI(km, lm); }
+                else if (fu) { my = 1; iya = MWI(kp, lm); iyb = MWI(km - 1, lm); }
+            }
+        }
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        // ---- wait for the window's earlier hole pixels that are still in flight; their colours arrive through the ring
+        unsigned spins = 0;
+        while (true) {
+            bool pend = false;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (pj[r] != NONE) {
+                    const unsigned long long s = *(volatile unsigned long long*)&sh.u.ring[pj[r] & (MARCH_RING - 1)];
+                    const unsigned tag = (unsigned)s;
+                    if (tag == pj[r] + 1u) { w.img[lane + 32 * r] = (unsigned)(s >> 32); pj[r] = NONE; }
+                    else if (tag > pj[r] + 1u) {     // entry reused by a later pixel: this one was final long ago
+                        __threadfence_block();
+                        const int idx = lane + 32 * r;
+                        const size_t q = (size_t)(y + idx / 9 - 4) * Ws + (x + idx % 9 - 4);
+                        w.img[idx] = *reinterpret_cast<volatile const unsigned*>(&V.img[q]);
+                        pj[r] = NONE;
+                    } else pend = true;
+                }
+            if (!__any_sync(0xffffffffu, pend)) break;
+            __nanosleep(20);
+            if (++spins > MARCH_WATCHDOG) { sh.flag = 2; break; }      // never in a correct run: fail loudly instead of hanging
+        }
+        __syncwarp();
+        // ---- icvTeleaInpaintFMM body: per-tap terms, then sums in the reference's raster order
+        if (valid) {
+            const unsigned pc = w.img[ic];
+            const unsigned pxa = w.img[ixa], pxb = w.img[ixb], pya = w.img[iya], pyb = w.img[iyb];
+            float* sm = w.taps + lane * 10;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int sh8 = 8 * c;
+                float gix = 0.f, giy = 0.f;
+                if (mx) { gix = (float)((int)((pxa >> sh8) & 0xffu) - (int)((pxb >> sh8) & 0xffu)); if (mx == 2) gix = __fmul_rn(gix, 2.0f); }
+                if (my) { giy = (float)((int)((pya >> sh8) & 0xffu) - (int)((pyb >> sh8) & 0xffu)); if (my == 2) giy = __fmul_rn(giy, 2.0f); }
+                sm[c] = __fmul_rn(wgt, (float)((pc >> sh8) & 0xffu));
+                sm[3 + c] = __fmul_rn(wgt, __fmul_rn(gix, rx));
+                sm[6 + c] = __fmul_rn(wgt, __fmul_rn(giy, ry));
+            }
+            sm[9] = wgt;
+        }
+        __syncwarp();
+        // lanes 0..9 each accumulate one quantity in tap order: Ia[3], Jx[3], Jy[3], s
+        // (adding +0 for an absent tap leaves the accumulator bit-identical: it is never -0)
+        float acc = lane == 9 ? 1.0e-20f : 0.f;
+        {
+            const int col = lane < 10 ? lane : 0;
+            const bool sub = lane >= 3 && lane < 9;
+            float t[28];
+#pragma unroll
+            for (int L = 0; L < 28; L++) t[L] = w.taps[L * 10 + col];
+#pragma unroll
+            for (int L = 0; L < 28; L++) {
+                const float tv = ((vm >> L) & 1u) ? t[L] : 0.f;
+                acc = sub ? __fsub_rn(acc, tv) : __fadd_rn(acc, tv);
+            }
+        }
+        const float s = __shfl_sync(0xffffffffu, acc, 9);
+        const float jx = __shfl_sync(0xffffffffu, acc, min(lane + 3, 31));
+        const float jy = __shfl_sync(0xffffffffu, acc, min(lane + 6, 31));
+        int outc = 0;
+        if (lane < 3) {
+            const float ia_s = __fdiv_rn(acc, s);
+            const float jsum = __fadd_rn(jx, jy);
+            const float jn = __fadd_rn(__fmul_rn(jx, jx), __fmul_rn(jy, jy));
+            const double den = __dadd_rn(sqrt((double)jn), (double)1.0e-20f);
+            const double val = __dadd_rn(__dadd_rn((double)ia_s, __ddiv_rn((double)jsum, den)), (double)0.5f);
+            const float sat = (float)val;
+            outc = min(max(__float2int_rn(sat), 0), 255);
+        }
+        const unsigned c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
+                       c2 = __shfl_sync(0xffffffffu, outc, 2);
+        if (lane == 0) {
+            const unsigned nv = (w.img[MWI(y, x)] & 0xff000000u) | c0 | (c1 << 8) | (c2 << 16);
+            *reinterpret_cast<unsigned*>(&V.img[p]) = nv;
+            // an entry may only be reused once its previous occupant (J - RING) is final
+            if (j >= MARCH_RING) {
+                unsigned spins2 = 0;
+                while (*(volatile unsigned*)&sh.done_prefix + (unsigned)MARCH_RING <= (unsigned)j) {
+                    __nanosleep(64);
+                    if (++spins2 > MARCH_WATCHDOG) { sh.flag = 2; break; }
+                }
+            }
+            __threadfence_block();
+            *(volatile unsigned long long*)&sh.u.ring[j & (MARCH_RING - 1)] = ((unsigned long long)nv << 32) | (unsigned long long)(unsigned)(j + 1);
+            // advance the finished prefix over everything that is final
+            unsigned d = *(volatile unsigned*)&sh.done_prefix;
+            const unsigned d0 = d;
+            while (d < (unsigned)ntask && (unsigned)*(volatile unsigned long long*)&sh.u.ring[d & (MARCH_RING - 1)] == d + 1u) d++;
+            if (d > d0) { __threadfence_block(); atomicMax(&sh.done_prefix, d); }
+        }
+        __syncwarp();
+#undef MWI
+    }
+    __syncthreads();
+}
+
+// One CTA per cluster (persistent CTAs pull clusters, big ones first).
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(const __grid_constant__ TeleaArgs a) {
+    extern __shared__ __align__(16) unsigned char march_smem[];
+    MarchSh<NW>& sh = *reinterpret_cast<MarchSh<NW>*>(march_smem);
+    const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
+    if (tid < 32) { sh.tp.dk[tid] = c_taps.dk[tid]; sh.tp.dl[tid] = c_taps.dl[tid]; sh.tp.dst[tid] = c_taps.dst[tid]; }
+    if (tid == 0) sh.flag = 0;
+    const int v = blockIdx.x;       // view-major launch order: the first CTAs to start take each view's biggest cluster
+    const TeleaView& V = a.v[v];
+    const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
+    if (V.fs->qbump[V.vi] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
+        if (tid == 0 && blockIdx.y == 0) atomicMax(&V.fs->overflow, V.fs->qbump[V.vi]);
+        return;
+    }
+    const int Hs = a.Hs, Ws = a.Ws, cap = a.tw * a.th;
+    unsigned* const scr0 = reinterpret_cast<unsigned*>(V.qkey[0]);     // 6 qcap-sized u32 arrays
+    unsigned* const scr1 = V.qidx[0];                                  // 3 more
+    __syncthreads();
+    while (true) {
+        if (tid == 0) sh.ci = atomicAdd(&V.fs->next[V.vi], 1);
+        __syncthreads();
+        const int i = sh.ci;
+        if (i >= ncl) break;
+        const int ci = i < nbig ? i : cap - 1 - (i - nbig);     // big clusters are queued first
+        const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
+        const int* tiles = V.tile_list + V.cl_toff[ci];
+        MarchScratch sc;
+        sc.band = scr0 + qoff; sc.L[0] = scr0 + (size_t)V.qcap + qoff; sc.L[1] = scr0 + 2 * (size_t)V.qcap + qoff;
+        sc.L[2] = scr0 + 3 * (size_t)V.qcap + qoff; sc.sa = scr0 + 4 * (size_t)V.qcap + qoff; sc.ka = scr0 + 5 * (size_t)V.qcap + qoff;
+        sc.kb = scr1 + qoff; sc.seq = scr1 + (size_t)V.qcap + qoff;
+        if (tid == 0) { sh.need_left = V.cl_size[ci]; sh.nband = 0; sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+        __syncthreads();
+        // the band (initial queue of both sweeps): collect, then order by raster position
+        for (int ti = wid; ti < ntiles; ti += NW) {
+            const int t = tiles[ti];
+            const int ty = t / a.tw, tx = t - ty * a.tw;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int y = ty * TG + (lane >> 3) + 4 * h, x = tx * TG + (lane & 7);
+                bool isb = false;
+                unsigned p = 0;
+                if (y < Hs && x < Ws) { p = (unsigned)y * (unsigned)Ws + (unsigned)x; isb = (V.st[p] & ST_BAND0) != 0; }
+                const unsigned bm = __ballot_sync(0xffffffffu, isb);
+                int base = 0;
+                if (lane == 0 && bm) base = atomicAdd(&sh.nband, __popc(bm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (isb) {
+                    const int pos = base + __popc(bm & ((1u << lane) - 1));
+                    sc.ka[pos] = p; sc.sa[pos] = p;
+                }
+                const unsigned pmn = __reduce_min_sync(0xffffffffu, isb ? p : 0xffffffffu), pmx = __reduce_max_sync(0xffffffffu, isb ? p : 0u);
+                if (lane == 0 && bm) { atomicMin(&sh.kmin, pmn); atomicMax(&sh.kmax, pmx); }
+            }
+        }
+        __syncthreads();
+        const int nband = sh.nband;
+        {
+            const unsigned kmin = sh.kmin, span = nband ? sh.kmax - kmin : 0u;
+            const int nbits = span ? 32 - __clz(span) : 0;
+            if (!radix_sort<NW>(sc.ka, sc.sa, sc.kb, sc.band, nband, nbits, kmin, sh)) {
+                for (int e = tid; e < nband; e += nt) sc.band[e] = sc.sa[e];
+                __syncthreads();
+            }
+        }
+        march_order<true, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        // icvCalcFMM(..., negate = true): the popped pixels of the outer sweep (band and ring) get T = -T
+        for (int ti = wid; ti < ntiles; ti += NW) {
+            const int t = tiles[ti];
+            const int ty = t / a.tw, tx = t - ty * a.tw;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int y = ty * TG + (lane >> 3) + 4 * h, x = tx * TG + (lane & 7);
+                if (y < Hs && x < Ws) {
+                    const size_t p = (size_t)y * Ws + x;
+                    const unsigned char s = V.st[p];
+                    if ((s & ST_BAND0) || (s & O_MASK) == O_INSIDE) V.tt[p] = -V.tt[p];
+                }
+            }
+        }
+        __syncthreads();
+        const int ntask = march_order<false, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        march_colour<NW>(V, sh, sc.seq, ntask, Hs, Ws);
+        if (tid == 0 && sh.flag) atomicMax(&V.fs->overflow, 0x7fffffff);    // broken bucket invariant: make the host fail loudly
+        __syncthreads();
+    }
+}
+
+}  // namespace vsc

@@ -103,7 +103,7 @@ def load():
     lib.vsc_timer_begin.argtypes = [vp]
     lib.vsc_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
     lib.vsc_debug_fetch.argtypes = [vp, i, vp, C.c_size_t]
-    lib.vsc_debug_telea_state.argtypes = [vp, i, vp, vp, C.c_size_t]
+    lib.vsc_debug_telea_state.argtypes = [vp, i, vp, vp, vp, C.c_size_t]
     lib.vsc_debug_telea_stats.argtypes = [vp, vp]
     lib.vsc_debug_set_telea_capacity.argtypes = [vp, C.c_size_t]
     if lib.vsc_abi_version() != 1:
