@@ -18,8 +18,11 @@ for n, t in gen.kernel_times(0):
     if t > 0.05: print(f'  {n:28s} {t:8.3f} ms')
 st = (C.c_ulonglong * 64)()
 _lib.check(lib.vsc_debug_telea_stats(gen._ctx.handle, st))
-names = ['c_wait', 'c_pop', 'c_sort', 'c_part', 'c_total', 'n_pops', 'n_pix', 'n_gen', 'n_polls', 'n_clusters', 'max_total', 'max_pops', 'max_c_load', 'max_c_min4', 'max_c_inp', 'max_c_rel']
+names = ['sum_total', 'n_clusters', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'tasks_holes', 'tasks_ring',
+         'max_total', 'max_band', 'max_outer', 'max_order', 'max_colour', 'max_ntask', 'max_nband', 'max_gens_holes',
+         'max_gens_ring', 'max_sweeps', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push', 'max_ntask_ring']
+cyc = {'sum_total', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'max_total', 'max_band', 'max_outer', 'max_order',
+       'max_colour', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push'}
 for v in range(2):
-    for p in range(2):
-        d = {names[i]: st[(v * 2 + p) * 16 + i] for i in range(16)}
-        print('view', v, 'outer' if p == 0 else 'main ', {k: (f'{x/1e6:.2f}Mcyc' if k.startswith('c_') or k.startswith('max_c') or k == 'max_total' else x) for k, x in d.items()})
+    d = {names[i]: st[v * 32 + i] for i in range(len(names))}
+    print('view', v, {k: (f'{x / 1e6:.3f}Mcyc' if k in cyc else x) for k, x in d.items()})

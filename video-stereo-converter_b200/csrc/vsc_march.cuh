@@ -48,6 +48,9 @@ template <int NW> struct MarchSh {
     int cnt[3];
     int need_left, ci, nband, next_task, flag;
     unsigned kmin, kmax, done_prefix;
+#ifdef VSC_TELEA_STATS
+    int st_gens, st_sweeps; long long st_sort, st_claim, st_sweep, st_push;
+#endif
     TapTable tp;
     MarchWin win[NW];
 };
@@ -139,6 +142,16 @@ __device__ int radix_sort(unsigned* k0, unsigned* v0, unsigned* k1, unsigned* v1
     return w;
 }
 
+#ifdef VSC_TELEA_STATS
+#define MSTAT(stmt_) do { if (threadIdx.x == 0) { stmt_; } } while (0)
+#define MSTAT_T0() long long mst_t = clock64()
+#define MSTAT_T1(f) do { if (threadIdx.x == 0) { const long long n_ = clock64(); sh.f += n_ - mst_t; mst_t = n_; } } while (0)
+#else
+#define MSTAT(stmt_)
+#define MSTAT_T0()
+#define MSTAT_T1(f)
+#endif
+
 // the reference's neighbour order: up, left, down, right
 __device__ __forceinline__ int nb_dy(int q) { return q == 0 ? -1 : (q == 2 ? 1 : 0); }
 __device__ __forceinline__ int nb_dx(int q) { return q == 1 ? -1 : (q == 3 ? 1 : 0); }
@@ -160,6 +173,8 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
         }
         unsigned* cur = g == 0 ? sc.band : sc.L[g % 3];
         const unsigned* S = cur;
+        MSTAT(sh.st_gens++);
+        MSTAT_T0();
         if (g > 0) {      // pop order of the bucket: stable sort by T (generation 0 is the band in raster order, all T = 0)
             if (tid == 0) { sh.kmin = 0xffffffffu; sh.kmax = 0u; }
             __syncthreads();
@@ -175,6 +190,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
             const int nbits = span ? 32 - __clz(span) : 0;
             if (radix_sort<NW>(sc.ka, cur, sc.kb, sc.sa, n, nbits, kmin, sh)) S = sc.sa;
         }
+        MSTAT_T1(st_sort);
         // claims: the first popped neighbour (lowest pop rank, then lowest q) computes a pixel
         for (int e = tid; e < n; e += nt) {
             const unsigned p = S[e];
@@ -228,9 +244,11 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
             }
         }
         __syncthreads();
+        MSTAT_T1(st_claim);
         // distances: re-evaluate until the (unique) fixed point
         while (true) {
             int ch = 0;
+            MSTAT(sh.st_sweeps++);
             for (int j = tid; j < ntask; j += nt) {
                 const unsigned p = TL[j], J = tbase + (unsigned)j;
                 const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
@@ -253,6 +271,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
             }
             if (!__syncthreads_or(ch)) break;
         }
+        MSTAT_T1(st_sweep);
         // push in task order: a stable split into the next two buckets
         const int b1i = (g + 1) % 3, b2i = (g + 2) % 3;
         const int tper = (ntask + nt - 1) / nt, j0 = min(ntask, tid * tper), j1 = min(ntask, j0 + tper);
@@ -285,6 +304,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
         }
         tbase += (unsigned)ntask;
         __syncthreads();
+        MSTAT_T1(st_push);
         // Everything still queued is farther from the hole boundary than every pixel computed so far and cannot influence
         // them; once all hole pixels inside the kept window are computed the rest of the cluster is never read.
         if (!OUTER && sh.need_left <= 0) break;
@@ -497,6 +517,10 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
         sc.L[2] = scr0 + 3 * (size_t)V.qcap + qoff; sc.sa = scr0 + 4 * (size_t)V.qcap + qoff; sc.ka = scr0 + 5 * (size_t)V.qcap + qoff;
         sc.kb = scr1 + qoff; sc.seq = scr1 + (size_t)V.qcap + qoff;
         if (tid == 0) { sh.need_left = V.cl_size[ci]; sh.nband = 0; sh.kmin = 0xffffffffu; sh.kmax = 0u; }
+#ifdef VSC_TELEA_STATS
+        long long ck[5];
+        if (tid == 0) { sh.st_gens = sh.st_sweeps = 0; sh.st_sort = sh.st_claim = sh.st_sweep = sh.st_push = 0; ck[0] = clock64(); }
+#endif
         __syncthreads();
         // the band (initial queue of both sweeps): collect, then order by raster position
         for (int ti = wid; ti < ntiles; ti += NW) {
@@ -530,7 +554,13 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
                 __syncthreads();
             }
         }
-        march_order<true, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        MSTAT(ck[1] = clock64());
+        const int ntask_outer = march_order<true, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        (void)ntask_outer;
+#ifdef VSC_TELEA_STATS
+        int gens_outer = 0;
+        if (tid == 0) { gens_outer = sh.st_gens; sh.st_gens = 0; }
+#endif
         // icvCalcFMM(..., negate = true): the popped pixels of the outer sweep (band and ring) get T = -T
         for (int ti = wid; ti < ntiles; ti += NW) {
             const int t = tiles[ti];
@@ -546,8 +576,26 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
             }
         }
         __syncthreads();
+        MSTAT(ck[2] = clock64());
         const int ntask = march_order<false, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        MSTAT(ck[3] = clock64());
         march_colour<NW>(V, sh, sc.seq, ntask, Hs, Ws);
+#ifdef VSC_TELEA_STATS
+        if (tid == 0 && a.stats) {
+            ck[4] = clock64();
+            unsigned long long* st = a.stats + (v & 1) * 32;
+            const unsigned long long tot = (unsigned long long)(ck[4] - ck[0]);
+            atomicAdd(&st[0], tot); atomicAdd(&st[1], 1ull);
+            atomicAdd(&st[2], (unsigned long long)(ck[1] - ck[0])); atomicAdd(&st[3], (unsigned long long)(ck[2] - ck[1]));
+            atomicAdd(&st[4], (unsigned long long)(ck[3] - ck[2])); atomicAdd(&st[5], (unsigned long long)(ck[4] - ck[3]));
+            atomicAdd(&st[6], (unsigned long long)ntask); atomicAdd(&st[7], (unsigned long long)ntask_outer);
+            if (tot > st[8]) {      // the slowest cluster (racy, good enough for a profile)
+                st[8] = tot; st[9] = ck[1] - ck[0]; st[10] = ck[2] - ck[1]; st[11] = ck[3] - ck[2]; st[12] = ck[4] - ck[3];
+                st[13] = ntask; st[14] = nband; st[15] = sh.st_gens; st[16] = gens_outer; st[17] = sh.st_sweeps;
+                st[18] = sh.st_sort; st[19] = sh.st_claim; st[20] = sh.st_sweep; st[21] = sh.st_push; st[22] = ntask_outer;
+            }
+        }
+#endif
         if (tid == 0 && sh.flag) atomicMax(&V.fs->overflow, 0x7fffffff);    // broken bucket invariant: make the host fail loudly
         __syncthreads();
     }
