@@ -19,6 +19,11 @@
  *                neighbours is not available up front; the (unique, because the dependencies follow J) fixed point
  *                is reached by re-evaluating all tasks until nothing changes ("sweeps").
  *
+ *   one march   = the outer-ring sweep and the hole sweep are independent (a ring pixel and a hole pixel are never
+ *                4-neighbours: the band separates them), start from the same band and use the same buckets, so the
+ *                GPU runs them as ONE march over the union of both domains.  The order restricted to the hole pixels
+ *                is the hole sweep's own order; ring times are negated afterwards (icvCalcFMM's negate).
+ *
  * This file restates that schedule sequentially, so that tests can pin it against the one-pop-at-a-time oracle
  * (orc_telea_u8c3 / orc_telea_u8c3_two_pass): identical T for every pixel, identical order for every hole pixel.
  * It also reports the shape of the work (generations, bucket sizes, sweeps) for DESIGN.md.
@@ -67,14 +72,14 @@ static int sent_cmp(const void *a, const void *b) {
 /* One fast-marching pass over the domain `dom` (1 = still to compute).  C = row pitch, the 1-pixel frame is
  * outside the domain and never popped.  band: initial queue in raster order (T = 0).  ord (optional): receives the
  * computation index of every domain pixel.  Returns the number of tasks. */
-static size_t march_pass(const uint8_t *dom, float *t, int R, int C, const list_t *band, int32_t *ord, int64_t *stats) {
+static size_t march_pass(const uint8_t *dom, const uint8_t *hole, float *t, int R, int C, const list_t *band, int32_t *ord, int64_t *stats) {
     const size_t N = (size_t)R * C;
     uint32_t *ow = malloc(N * sizeof(uint32_t)); /* 0xffffffff: not computed; < 2^31: task index J; else a claim */
     for (size_t k = 0; k < N; k++) ow[k] = 0xffffffffu;
     list_t B[3] = {{0}, {0}, {0}};
     for (size_t k = 0; k < band->n; k++) lpush(&B[0], band->p[k]);
     const int dq[4] = {-C, -1, C, 1}; /* up, left, down, right: the reference's neighbour order */
-    size_t tbase = 0;
+    size_t tbase = 0, nhole = 0;
     sent *srt = NULL; size_t srt_cap = 0;
     uint32_t *tl = NULL; size_t tl_cap = 0;
     float *tprev = NULL; size_t tprev_cap = 0;
@@ -152,7 +157,7 @@ static size_t march_pass(const uint8_t *dom, float *t, int R, int C, const list_
             const int b = (int)floorf(t[p] * BUCKET_W_INV);
             if (b != g + 1 && b != g + 2) { stats[0] = -1000000 - g; goto out; } /* the bucket argument failed */
             lpush(&B[b % 3], p);
-            if (ord) ord[p] = (int32_t)(tbase + j);
+            if (ord && hole[p]) ord[p] = (int32_t)nhole++;   /* index among the hole pixels, in computation order */
         }
         tbase += ntask;
         cur->n = 0;
@@ -165,14 +170,14 @@ out:
 }
 
 /* mask [H,W] nonzero = hole (already dilated).  t_out [(H+2)*(W+2)] as orc_telea_u8c3's t_out; ord_out
- * [(H+2)*(W+2)] as orc_telea_u8c3_two_pass's ord_out (-1 outside the mask); stats [2][NSTAT]: outer pass, main pass */
+ * [(H+2)*(W+2)] as orc_telea_u8c3_two_pass's ord_out (-1 outside the mask); stats [NSTAT] */
 ORC_API void orc_march_model(const uint8_t *mask, int H, int W, int radius, float *t_out, int32_t *ord_out, int64_t *stats) {
     const int R = H + 2, C = W + 2;
     const int range = radius < 1 ? 1 : (radius > 100 ? 100 : radius);
     const size_t N = (size_t)R * C;
     uint8_t *f = calloc(N, 1), *o = calloc(N, 1), *bnd = calloc(N, 1);
     float *t = malloc(N * sizeof(float));
-    memset(stats, 0, 2 * NSTAT * sizeof(int64_t));
+    memset(stats, 0, NSTAT * sizeof(int64_t));
     for (size_t k = 0; k < N; k++) { t[k] = 1.0e6f; if (ord_out) ord_out[k] = -1; }
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++)
@@ -199,11 +204,13 @@ ORC_API void orc_march_model(const uint8_t *mask, int H, int W, int radius, floa
             if (hit) o[p] = 1;
         }
     if (band.n) {
-        march_pass(o, t, R, C, &band, NULL, stats);
-        /* icvCalcFMM(..., negate = true): every popped pixel (band and ring) gets t = -t */
-        for (size_t k = 0; k < N; k++) if (bnd[k] || (o[k] && t[k] != 1.0e6f)) t[k] = -t[k];
+        uint8_t *dom = malloc(N);
+        for (size_t k = 0; k < N; k++) dom[k] = (uint8_t)(o[k] | f[k]);
         if (ord_out) for (size_t k = 0; k < N; k++) if (f[k]) ord_out[k] = INT32_MAX;
-        march_pass(f, t, R, C, &band, ord_out, stats + NSTAT);
+        march_pass(dom, f, t, R, C, &band, ord_out, stats);
+        /* icvCalcFMM(..., negate = true): every popped pixel of the outer sweep (band and ring) gets t = -t */
+        for (size_t k = 0; k < N; k++) if (bnd[k] || (o[k] && t[k] != 1.0e6f)) t[k] = -t[k];
+        free(dom);
     }
     if (t_out) memcpy(t_out, t, N * sizeof(float));
     free(f); free(o); free(bnd); free(t); free(band.p);

