@@ -16,10 +16,17 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-sys.path[:0] = [HERE, os.path.join(ROOT, 'video-stereo-converter_b200')]
+sys.path.insert(0, HERE)      # NOT the product directory: its drop-in `helper` package must never be importable here
+
+import importlib.util  # noqa: E402
 
 import ref_runner  # noqa: E402
-from vsc_b200.synthetic import make_pair  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location(
+    'vsc_synthetic', os.path.join(ROOT, 'video-stereo-converter_b200', 'vsc_b200', 'synthetic.py'))
+_syn = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_syn)
+make_pair = _syn.make_pair
 
 CASES = {
     'default_u8': ((120, 160), np.uint8, 7, {}),

@@ -13,6 +13,7 @@ the CUDA path can be compared in isolation.
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 import sys
 from typing import Any, Dict
@@ -20,28 +21,53 @@ from typing import Any, Dict
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get('VSC_REFERENCE_ROOT', '/root/reference')
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'refshim')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, 'refshim')
+STAGED_ROOT = os.path.join(_HERE, '_ref')          # git-ignored copy made by oracle/make_ref.py (travels to the GPU box)
+_module = None
+
+
+def _roots():
+    return [r for r in (REFERENCE_ROOT, STAGED_ROOT) if os.path.isfile(os.path.join(r, 'helper', 'stereo_core.py'))]
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'helper', 'stereo_core.py'))
+    return bool(_roots())
+
+
+def reference_origin() -> str:
+    """'/root/reference', the staged copy, or '' - where import_reference() loads the module from."""
+    r = _roots()
+    return r[0] if r else ''
 
 
 def import_reference():
-    """Import the reference's helper.stereo_core (unmodified) and return the module."""
-    if not reference_available():
-        raise RuntimeError('reference tree not mounted at ' + REFERENCE_ROOT)
-    for p in (_SHIM, REFERENCE_ROOT):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    # a product-side drop-in package is also called `helper`; make sure we get the reference's
-    for name in list(sys.modules):
-        if name == 'helper' or name.startswith('helper.'):
-            mod = sys.modules[name]
-            f = getattr(mod, '__file__', '') or ''
-            if not f.startswith(REFERENCE_ROOT):
-                del sys.modules[name]
-    return importlib.import_module('helper.stereo_core')
+    """Load the reference's helper/stereo_core.py (unmodified) BY FILE PATH and return the module.
+
+    Loading by path (not `import helper.stereo_core`) matters: the product ships a drop-in package that is also
+    called `helper`, and a regular package always wins over the reference's namespace package, whatever the order of
+    sys.path.  The only name injected is `kornia` (the shim), because kornia is not installed."""
+    global _module
+    if _module is not None:
+        return _module
+    roots = _roots()
+    if not roots:
+        raise RuntimeError(f'reference not found at {REFERENCE_ROOT} nor staged at {STAGED_ROOT} (python oracle/make_ref.py)')
+    path = os.path.join(roots[0], 'helper', 'stereo_core.py')
+    if 'kornia' not in sys.modules:
+        shim_dir = _SHIM if os.path.isdir(os.path.join(_SHIM, 'kornia')) else roots[0]
+        spec = importlib.util.spec_from_file_location('kornia', os.path.join(shim_dir, 'kornia', '__init__.py'),
+                                                      submodule_search_locations=[os.path.join(shim_dir, 'kornia')])
+        kornia = importlib.util.module_from_spec(spec)
+        sys.modules['kornia'] = kornia
+        spec.loader.exec_module(kornia)
+    spec = importlib.util.spec_from_file_location('vsc_reference_stereo_core', path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['vsc_reference_stereo_core'] = mod       # dataclasses looks the module up by name
+    spec.loader.exec_module(mod)
+    assert os.path.abspath(mod.__file__).startswith(os.path.abspath(roots[0])), mod.__file__
+    _module = mod
+    return mod
 
 
 def run_reference(rgb: np.ndarray, depth: np.ndarray, params: Dict[str, float] | None = None,

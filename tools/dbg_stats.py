@@ -21,9 +21,9 @@ _lib.check(lib.vsc_debug_telea_stats(gen._ctx.handle, st))
 names = ['sum_total', 'n_clusters', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'tasks_holes', 'tasks_ring',
          'max_total', 'max_band', 'max_outer', 'max_order', 'max_colour', 'max_ntask', 'max_nband', 'max_gens_holes',
          'max_streams', 'max_sweeps', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push',
-         'b_prologue', 'b_wait', 'b_compute', 'b_tasks_with_pending', 'b_spins', 'b_global_polls', 'b_claim']
+         'b_load', 'b_terms', 'b_sums', 'b_final', 'b_release', 'b_handover', 'b_idle', 'b_tasks', 'b_continued']
 cyc = {'sum_total', 'sum_band', 'sum_outer', 'sum_order', 'sum_colour', 'max_total', 'max_band', 'max_outer', 'max_order',
-       'max_colour', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push', 'b_prologue', 'b_wait', 'b_compute', 'b_claim'}
+       'max_colour', 'max_c_sort', 'max_c_claim', 'max_c_sweep', 'max_c_push', 'b_load', 'b_terms', 'b_sums', 'b_final', 'b_release', 'b_handover', 'b_idle'}
 for v in range(2):
     d = {names[i]: st[v * 32 + i] for i in range(len(names))}
     print('view', v, {k: (f'{x / 1e6:.3f}Mcyc' if k in cyc else x) for k, x in d.items()})

@@ -669,21 +669,11 @@ static int run_telea(vsc_ctx* ctx, Slot& s, int Hs, int Ws, const ViewSpec* vs, 
     // persistent CTAs pulling clusters from a per-view queue (big clusters first); view-major launch order, so the
     // first CTAs to start take each view's biggest cluster
     dim3 cgrid(nviews, ctx->sm_count / 2);
-    static const int march_impl = getenv("VSC_MARCH_OLD") ? 0 : 1;      // A/B switch while the generation march is new
-    if (march_impl) {
-        prof_begin(s, "telea_march_kernel");
-        if (ctx->slots.size() == (size_t)ctx->group_size)     // one slot: nothing overlaps the march, favour its latency
-            telea_march_kernel<32><<<cgrid, 32 * 32, sizeof(MarchSh<32>), s.stream>>>(a);
-        else
-            telea_march_kernel<16><<<cgrid, 16 * 32, sizeof(MarchSh<16>), s.stream>>>(a);
-        KCHECK(s);
-        return VSC_OK;
-    }
-    prof_begin(s, "telea_cluster_kernel");
+    prof_begin(s, "telea_march_kernel");
     if (ctx->slots.size() == (size_t)ctx->group_size)     // one slot: nothing overlaps the march, favour its latency
-        telea_cluster_kernel<TELEA_WARPS_LATENCY><<<cgrid, TELEA_WARPS_LATENCY * 32, 0, s.stream>>>(a);
+        telea_march_kernel<32><<<cgrid, 32 * 32, sizeof(MarchSh<32>), s.stream>>>(a);
     else
-        telea_cluster_kernel<TELEA_WARPS_THROUGHPUT><<<cgrid, TELEA_WARPS_THROUGHPUT * 32, 0, s.stream>>>(a);
+        telea_march_kernel<16><<<cgrid, 16 * 32, sizeof(MarchSh<16>), s.stream>>>(a);
     KCHECK(s);
 #endif
     return VSC_OK;

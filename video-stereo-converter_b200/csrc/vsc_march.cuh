@@ -27,17 +27,8 @@
 
 namespace vsc {
 
-constexpr int MARCH_RING = 2048;                       // entries of the completion / colour ring (power of two)
 constexpr float MARCH_BUCKET_INV = 1.4285714285714286f; // 1 / 0.7 (bucket width < 1/sqrt(2), see header)
-constexpr int MARCH_MAX_STREAMS = 96;                  // generations with their own stage-B stream (later ones share the last)
-#ifndef VSC_MARCH_STREAM_WARPS
-#define VSC_MARCH_STREAM_WARPS 4
-#endif
-#ifndef VSC_MARCH_SLEEP_NS
-#define VSC_MARCH_SLEEP_NS 20
-#endif
-constexpr int MARCH_STREAM_WARPS = VSC_MARCH_STREAM_WARPS;   // warps that work on one stream at a time
-constexpr unsigned MARCH_WATCHDOG = 1u << 24;          // polls before a wait gives up and reports an error (seconds)
+constexpr int MARCH_SMEM_COUNTERS = 32768;
 
 struct MarchWin {            // per-warp 9x9 window around the pixel being inpainted
     unsigned img[81];
@@ -49,7 +40,7 @@ struct MarchWin {            // per-warp 9x9 window around the pixel being inpai
 template <int NW> struct MarchSh {
     union {
         unsigned hist[NW][256];                  // stage A: per-warp radix histograms
-        unsigned long long ring[MARCH_RING];     // stage B: (colour << 32) | (J + 1) once pixel J is final
+        unsigned char cnt[MARCH_SMEM_COUNTERS];  // stage B: dependency counters (bytes) of a cluster with that many tasks at most
     } u;
     unsigned tot[256];
     int wsum[32];
@@ -57,16 +48,10 @@ template <int NW> struct MarchSh {
     int rcnt[3];             // ring entries per bucket list (the early stop must not leave ring pixels behind)
     int need_left, ci, nband, flag;
     unsigned kmin, kmax;
-    int ns;                                   // stage B streams: generation k's hole tasks are seq[gs[k] .. gs[k+1])
-    int gs[MARCH_MAX_STREAMS + 2];
-    unsigned gj[MARCH_MAX_STREAMS + 2];       // task index J at which each stream starts (a dependency d >= gj[k] is in stream k or later)
-    int cursor[MARCH_MAX_STREAMS + 1], seats[MARCH_MAX_STREAMS + 1];
-    unsigned long long wbar[NW];              // one mbarrier per warp: a waiting warp sleeps on it, the finisher of its dependency arrives
-    unsigned wpar[NW];                        // its phase parity, carried from cluster to cluster
-    unsigned wtab[MARCH_RING];                // who waits for task J: ((J + 1) << 6) | warp, at entry J % RING (0 = nobody)
+    int rq_head, rq_tail, ndone;              // stage B: ready list cursors, finished tasks
 #ifdef VSC_TELEA_STATS
     int st_gens, st_sweeps; long long st_sort, st_claim, st_sweep, st_push;
-    unsigned long long b_pro, b_wait, b_comp, b_npend, b_spins, b_glob, b_claim;
+    unsigned long long b_ph[7], b_n, b_cont;
 #endif
     TapTable tp;
     MarchWin win[NW];
@@ -172,17 +157,6 @@ __device__ int radix_sort(unsigned* k0, unsigned* v0, unsigned* k1, unsigned* v1
 #define MSTAT_T1(f)
 #endif
 
-// sleep on an mbarrier until its current phase completes or ~ns nanoseconds have passed; true = the phase completed
-__device__ __forceinline__ bool mbar_try_wait_timed(unsigned long long* mbar, unsigned parity, unsigned ns) {
-    unsigned done;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(smem_addr(mbar)), "r"(parity), "r"(ns) : "memory");
-    return done != 0u;
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(mbar)) : "memory");
-}
-
 // the reference's neighbour order: up, left, down, right
 __device__ __forceinline__ int nb_dy(int q) { return q == 0 ? -1 : (q == 2 ? 1 : 0); }
 __device__ __forceinline__ int nb_dx(int q) { return q == 1 ? -1 : (q == 3 ? 1 : 0); }
@@ -191,8 +165,7 @@ __device__ __forceinline__ int nb_dx(int q) { return q == 1 ? -1 : (q == 3 ? 1 :
 // The two sweeps of the reference are independent (a ring pixel and a hole pixel are never 4-neighbours, the band
 // separates them), start from the same band and use the same buckets: they run as ONE march.  The order restricted to
 // the hole pixels is the hole sweep's own order.  Order word (V.pstate) of a computed pixel = its task index J.
-// Returns the number of hole tasks; sc.seq[0..) lists them in order, sh.gs[] holds the start of every generation's
-// slice (the "streams" of stage B).
+// Returns the number of hole tasks; sc.seq[0..) lists them in order.
 __device__ __forceinline__ bool march_dom(unsigned char s) { return (s & F_MASK) == F_INSIDE || (s & O_MASK) == O_INSIDE; }
 
 struct MarchEval { unsigned p; float tn[4]; bool in_[4]; float own; };
@@ -221,7 +194,7 @@ __device__ __forceinline__ float march_eval_min4(const MarchEval& e) {
 template <int NW>
 __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScratch& sc, int nband, int Hs, int Ws, int keep_x0, int keep_x1) {
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31;
-    if (tid == 0) { sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = 0; sh.rcnt[0] = sh.rcnt[1] = sh.rcnt[2] = 0; sh.ns = 0; sh.gs[0] = 0; }
+    if (tid == 0) { sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = 0; sh.rcnt[0] = sh.rcnt[1] = sh.rcnt[2] = 0; }
     __syncthreads();
     unsigned tbase = 0;
     int mtot = 0;            // hole tasks so far
@@ -361,10 +334,6 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
             __syncthreads();
             if (tid == 0) {
                 sh.cnt[b1i] = base1 + total1; sh.cnt[b2i] = ntask - total1; sh.cnt[g % 3] = 0; sh.rcnt[g % 3] = 0;
-                if (totalm) {       // a stream of stage B; generations beyond the table join the last stream
-                    if (sh.ns < MARCH_MAX_STREAMS) { sh.gj[sh.ns] = tbase; sh.ns++; }
-                    sh.gs[sh.ns] = mtot + totalm;
-                }
             }
         }
         tbase += (unsigned)ntask;
@@ -380,83 +349,122 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
 }
 
 // ---- stage B: colours in the recorded order --------------------------------------------------------------------
-// A finished hole pixel is stored with bit 31 (top of the otherwise unused validity byte) set, colour and "final" in
-// ONE 32-bit word: a reader needs no fence, a stale cached copy only says "not yet".  The ring is a direct-mapped
-// cache of recent results in shared memory, keyed by the task index.
-// Streams: the tasks of one generation form a stream that is worked off in order by up to MARCH_STREAM_WARPS warps;
-// later generations follow the earlier ones like wavefronts instead of queueing behind ALL of their tasks.  A warp
-// joins the lowest stream that still has unclaimed tasks and a free seat and stays until the stream is used up, so
-// the lowest unfinished stream is always served and every wait ends.
-constexpr unsigned MARCH_FINAL = 0x80000000u;
+// Inpainting pixel i reads the colours of the EARLIER hole pixels (order word < i) inside its 9x9 window (28 taps of the
+// radius-3 disc plus their 4-neighbours for the image gradients).  Stage B runs that dependency graph as a dataflow:
+//   * every task gets a counter = number of earlier hole pixels in its window; tasks with counter 0 seed the ready list
+//   * a warp takes a READY task, so it never waits for another task: load the window, weights, sums, colour
+//   * finishing a task decrements the counters of the later hole pixels in its window; the first one that reaches zero is
+//     taken over by the same warp at once (a crack is a chain: no hand-over latency), the others go to the ready list
+// Any topological order gives the reference's result, because each colour depends on its predecessors' colours only.
+// Idle warps look at the ready list every few hundred nanoseconds; they are not on anybody's critical path.
+// Counters are bytes in shared memory (a window has 80 other pixels) when the cluster's tasks fit, else words in global
+// memory.  Colours written by other warps are read with L1-bypassing loads after the counter handshake.
+constexpr unsigned MARCH_NONE = 0xffffffffu;
 template <int NW>
-__device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned* seq, int ntask, int Hs, int Ws) {
+__device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const MarchScratch& sc, int ntask, int Hs, int Ws) {
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
+    if (ntask <= 0) return;
     MarchWin& w = sh.win[wid];
-    for (int i = tid; i < MARCH_RING; i += nt) { sh.u.ring[i] = 0ull; sh.wtab[i] = 0u; }
-    for (int i = tid; i <= MARCH_MAX_STREAMS; i += nt) { sh.cursor[i] = 0; sh.seats[i] = 0; }
+    const unsigned* seq = sc.seq;
+    unsigned* const rq = sc.L[0];             // ready list: every task is appended at most once
+    unsigned* const gcnt = sc.L[1];           // counters when they do not fit into shared memory
+    unsigned char* const scnt = reinterpret_cast<unsigned char*>(&sh.u);
+    const bool small = ntask <= MARCH_SMEM_COUNTERS;
+    // ---- order words become indices into seq; ready list and counters are reset
+    for (int i = tid; i < ntask; i += nt) { V.pstate[seq[i]] = (unsigned)i; rq[i] = MARCH_NONE; }
+    if (tid == 0) { sh.rq_head = 0; sh.rq_tail = 0; sh.ndone = 0; }
     __syncthreads();
-    const int ns = sh.ns;
-    constexpr unsigned NONE = 0xffffffffu;
-    int strm = -1;
-    unsigned par = sh.wpar[wid];
-#ifdef VSC_TELEA_STATS
-    long long bt_prev = clock64();
-#endif
-    while (true) {
-        // ---- claim the next task of my stream (or join a stream)
-        int i = 0;
-        if (lane == 0) {
-            while (true) {
-                if (strm < 0) {
-                    int pick = -1;
-                    for (int k = 0; k < ns && pick < 0; k++)
-                        if (*(volatile int*)&sh.cursor[k] < sh.gs[k + 1] - sh.gs[k] && *(volatile int*)&sh.seats[k] < MARCH_STREAM_WARPS) pick = k;
-                    for (int k = 0; k < ns && pick < 0; k++)
-                        if (*(volatile int*)&sh.cursor[k] < sh.gs[k + 1] - sh.gs[k]) pick = k;
-                    if (pick < 0) { i = -1; break; }
-                    atomicAdd(&sh.seats[pick], 1);
-                    strm = pick;
-                }
-                i = atomicAdd(&sh.cursor[strm], 1);
-                if (i < sh.gs[strm + 1] - sh.gs[strm]) { i += sh.gs[strm]; break; }
-                strm = -1;
-            }
-        }
-        i = __shfl_sync(0xffffffffu, i, 0);
-        strm = __shfl_sync(0xffffffffu, strm, 0);
-        if (i < 0) break;
-#ifdef VSC_TELEA_STATS
-        const long long bt0 = clock64();
-        if (lane == 0) atomicAdd(&sh.b_claim, (unsigned long long)(bt0 - bt_prev));
-#endif
+    // ---- counters: one warp per task
+    for (int i = wid; i < ntask; i += NW) {
         const unsigned p = seq[i];
         const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
-        const unsigned j = V.pstate[p];               // my index in the computation order
-        unsigned pj[3];
+        int c = 0;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int idx = lane + 32 * r;
-            pj[r] = NONE;
-            if (idx < 81) {
+            bool dep = false;
+            if (idx < 81 && idx != 40) {
                 const int yy = y + idx / 9 - 4, xx = x + idx % 9 - 4;
-                unsigned c = 0; float t = 1.0e6f; unsigned char kn = 1;
                 if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
                     const size_t q = (size_t)yy * Ws + xx;
-                    const unsigned char s = V.st[q];
-                    t = V.tt[q];
-                    c = *reinterpret_cast<const unsigned*>(&V.img[q]);
-                    if ((s & F_MASK) == F_INSIDE) {
-                        const unsigned o = V.pstate[q];
-                        kn = o < j;
-                        if (kn && !(c & MARCH_FINAL)) pj[r] = o;      // computed before me but not final yet (as far as I see)
-                    }
+                    dep = (V.st[q] & F_MASK) == F_INSIDE && V.pstate[q] < (unsigned)i;
                 }
-                w.kn[idx] = kn; w.tt[idx] = t; w.img[idx] = c;
+            }
+            c += __popc(__ballot_sync(0xffffffffu, dep));
+        }
+        if (lane == 0) {
+            if (small) scnt[i] = (unsigned char)c; else gcnt[i] = (unsigned)c;
+            if (c == 0) rq[atomicAdd(&sh.rq_tail, 1)] = (unsigned)i;
+        }
+    }
+    __syncthreads();
+#ifdef VSC_TELEA_STATS
+    long long bts[7], bt_end = clock64();
+#define BSTAT(k) bts[k] = clock64()
+#else
+#define BSTAT(k)
+#endif
+    unsigned next = MARCH_NONE;               // task handed over by the one I just finished
+    unsigned prevp = 0, prevc = 0;            // its pixel and colour (my own store may not have reached L2 yet)
+    while (true) {
+        unsigned i = next;
+        if (i == MARCH_NONE) {
+            if (lane == 0) {
+                const int h = atomicAdd(&sh.rq_head, 1);
+                while (true) {
+                    if (h < *(volatile int*)&sh.rq_tail) {
+                        i = *reinterpret_cast<volatile unsigned*>(&rq[h]);
+                        if (i != MARCH_NONE) break;
+                    } else if (*(volatile int*)&sh.ndone >= ntask) break;
+                    __nanosleep(200);
+                }
+            }
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i == MARCH_NONE) break;
+        }
+        __threadfence_block();                 // counters / ready list first, then the colours they announce
+        BSTAT(0);
+        const unsigned p = seq[i];
+        const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+        unsigned po[3];                        // order words of the hole pixels of the window (NONE elsewhere)
+        {
+            // all twelve loads of a lane are issued before the first use (one memory round trip); positions outside the
+            // image read a clamped address and are discarded.  Order words are initialised wherever a window can reach.
+            size_t qa[3]; bool inimg[3];
+            unsigned char sv[3]; float tv[3]; unsigned cv[3], ov[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int idx = min(lane + 32 * r, 80);
+                const int yy = y + idx / 9 - 4, xx = x + idx % 9 - 4;
+                inimg[r] = yy >= 0 && yy < Hs && xx >= 0 && xx < Ws;
+                qa[r] = (size_t)min(max(yy, 0), Hs - 1) * Ws + min(max(xx, 0), Ws - 1);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                sv[r] = V.st[qa[r]]; tv[r] = V.tt[qa[r]]; ov[r] = V.pstate[qa[r]];
+                cv[r] = __ldcg(reinterpret_cast<const unsigned*>(&V.img[qa[r]]));
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int idx = lane + 32 * r;
+                po[r] = MARCH_NONE;
+                if (idx < 81) {
+                    unsigned c = 0; float t = 1.0e6f; unsigned char kn = 1;
+                    if (inimg[r]) {
+                        t = tv[r]; c = cv[r];
+                        if ((sv[r] & F_MASK) == F_INSIDE) {
+                            kn = ov[r] < i;
+                            po[r] = ov[r];
+                            if ((unsigned)qa[r] == prevp && next != MARCH_NONE) c = prevc;
+                        }
+                    }
+                    w.kn[idx] = kn; w.tt[idx] = t; w.img[idx] = c;
+                }
             }
         }
         __syncwarp();
+        BSTAT(1);
 #define MWI(yy, xx) (((yy) - y + 4) * 9 + ((xx) - x + 4))
-        // ---- everything that does not depend on colours: gradient of T, the 28 weights, which pixels each tap reads
         const float dist = w.tt[MWI(y, x)];
         float gtx, gty;
         {
@@ -466,95 +474,44 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
             if (d) gty = u ? __fmul_rn(__fsub_rn(w.tt[MWI(y + 1, x)], w.tt[MWI(y - 1, x)]), 0.5f) : __fsub_rn(w.tt[MWI(y + 1, x)], dist);
             else gty = u ? __fsub_rn(dist, w.tt[MWI(y - 1, x)]) : 0.f;
         }
+        // ---- icvTeleaInpaintFMM body: one tap per lane, then sums in the reference's raster order
         bool valid = false;
-        float wgt = 0.f, rx = 0.f, ry = 0.f;
-        int ic = 0, ixa = 0, ixb = 0, iya = 0, iyb = 0, mx = 0, my = 0;     // mx / my: 0 none, 1 one-sided, 2 central (x2)
         if (lane < 28) {
             const int dk = sh.tp.dk[lane], dl = sh.tp.dl[lane];
             const int ky = y + dk, kx = x + dl;
             if (ky >= 0 && ky < Hs && kx >= 0 && kx < Ws && w.kn[MWI(ky, kx)]) {
                 valid = true;
-                ry = (float)(-dk); rx = (float)(-dl);
-                const float lev = (float)__ddiv_rn(1.0, __dadd_rn(1.0, fabs((double)__fsub_rn(w.tt[MWI(ky, kx)], dist))));
+                const float ry = (float)(-dk), rx = (float)(-dl);
+                const float lev = (float)__drcp_rn(__dadd_rn(1.0, fabs((double)__fsub_rn(w.tt[MWI(ky, kx)], dist))));     // 1/x correctly rounded = 1.0/x
                 float dir = __fadd_rn(__fmul_rn(rx, gtx), __fmul_rn(ry, gty));
-                if (fabs((double)dir) <= 0.01) dir = 0.000001f;
-                wgt = fabsf(__fmul_rn(__fmul_rn(sh.tp.dst[lane], lev), dir));
+                if (fabsf(dir) <= 0.01f) dir = 0.000001f;     // 0.01f is the largest float <= 0.01: same as the reference's double compare
+                const float wgt = fabsf(__fmul_rn(__fmul_rn(sh.tp.dst[lane], lev), dir));
                 const bool fr = w.kn[MWI(ky, kx + 1)], fl = w.kn[MWI(ky, kx - 1)], fd = w.kn[MWI(ky + 1, kx)], fu = w.kn[MWI(ky - 1, kx)];
                 const int km = ky + (ky == 0), kp = ky - (ky == Hs - 1);
                 const int lm = kx + (kx == 0), lp = kx - (kx == Ws - 1);
-                ic = MWI(ky, kx);
+                int ixa = 0, ixb = 0, iya = 0, iyb = 0, mx = 0, my = 0;     // mx / my: 0 none, 1 one-sided, 2 central (x2)
                 if (fr) { mx = fl ? 2 : 1; ixa = MWI(km, lp + 1); ixb = fl ? MWI(km, lm - 1) : MWI(km, lm); }
                 else if (fl) { mx = 1; ixa = MWI(km, lp); ixb = MWI(km, lm - 1); }
                 if (fd) { my = fu ? 2 : 1; iya = MWI(kp + 1, lm); iyb = fu ? MWI(km - 1, lm) : MWI(km, lm); }
                 else if (fu) { my = 1; iya = MWI(kp, lm); iyb = MWI(km - 1, lm); }
+                const unsigned pc = w.img[MWI(ky, kx)];
+                const unsigned pxa = w.img[ixa], pxb = w.img[ixb], pya = w.img[iya], pyb = w.img[iyb];
+                float* sm = w.taps + lane * 10;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int sh8 = 8 * c;
+                    float gix = 0.f, giy = 0.f;
+                    if (mx) { gix = (float)((int)((pxa >> sh8) & 0xffu) - (int)((pxb >> sh8) & 0xffu)); if (mx == 2) gix = __fmul_rn(gix, 2.0f); }
+                    if (my) { giy = (float)((int)((pya >> sh8) & 0xffu) - (int)((pyb >> sh8) & 0xffu)); if (my == 2) giy = __fmul_rn(giy, 2.0f); }
+                    sm[c] = __fmul_rn(wgt, (float)((pc >> sh8) & 0xffu));
+                    sm[3 + c] = __fmul_rn(wgt, __fmul_rn(gix, rx));
+                    sm[6 + c] = __fmul_rn(wgt, __fmul_rn(giy, ry));
+                }
+                sm[9] = wgt;
             }
         }
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        // ---- wait for the window's earlier hole pixels that are still in flight, one at a time.  A result is looked up in
-        // the ring, then in global memory; if it is not there yet the warp SLEEPS on its mbarrier (no issue slots spent):
-        // a dependency in my own stream - the chain I am part of - is announced in wtab and its finisher wakes me, anything
-        // else (an earlier generation's wavefront) is re-examined after a short timed sleep.
-#ifdef VSC_TELEA_STATS
-        const long long bt1 = clock64();
-        const bool anyp = __any_sync(0xffffffffu, pj[0] != NONE || pj[1] != NONE || pj[2] != NONE);
-        unsigned nglob = 0, spins = 0;
-#endif
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            unsigned m = __ballot_sync(0xffffffffu, pj[r] != NONE);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned d = __shfl_sync(0xffffffffu, pj[r], src);
-                const int idx = src + 32 * r;
-                if (lane == 0) {
-                    const size_t q = (size_t)(y + idx / 9 - 4) * Ws + (x + idx % 9 - 4);
-                    const bool same = d >= sh.gj[strm];
-                    const unsigned reg = ((d + 1u) << 6) | (unsigned)wid;
-                    unsigned* const slot = &sh.wtab[d & (MARCH_RING - 1)];
-                    bool registered = false;
-                    unsigned colour = 0;
-                    for (unsigned it = 0;; it++) {
-                        const unsigned long long s = *(volatile unsigned long long*)&sh.u.ring[d & (MARCH_RING - 1)];
-                        if ((unsigned)s == d + 1u) { colour = (unsigned)(s >> 32); break; }
-                        const unsigned c = *reinterpret_cast<volatile const unsigned*>(&V.img[q]);
-                        MSTAT_ANY(nglob++);
-                        if (c & MARCH_FINAL) { colour = c; break; }
-                        if (same && !registered) {
-                            registered = atomicCAS(slot, 0u, reg) == 0u;
-                            if (registered) continue;             // look again before sleeping: the finisher may just have passed
-                        }
-                        if (mbar_try_wait_timed(&sh.wbar[wid], par, registered ? 4000u : 400u)) par ^= 1u;
-                        MSTAT_ANY(spins++);
-                        if (it > MARCH_WATCHDOG) { sh.flag = 2; break; }      // never in a correct run: fail loudly instead of hanging
-                    }
-                    if (registered) atomicCAS(slot, reg, 0u);
-                    w.img[idx] = colour;
-                }
-            }
-        }
-        __syncwarp();
-#ifdef VSC_TELEA_STATS
-        const long long bt2 = clock64();
-#endif
-        // ---- icvTeleaInpaintFMM body: per-tap terms, then sums in the reference's raster order
-        if (valid) {
-            const unsigned pc = w.img[ic];
-            const unsigned pxa = w.img[ixa], pxb = w.img[ixb], pya = w.img[iya], pyb = w.img[iyb];
-            float* sm = w.taps + lane * 10;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int sh8 = 8 * c;
-                float gix = 0.f, giy = 0.f;
-                if (mx) { gix = (float)((int)((pxa >> sh8) & 0xffu) - (int)((pxb >> sh8) & 0xffu)); if (mx == 2) gix = __fmul_rn(gix, 2.0f); }
-                if (my) { giy = (float)((int)((pya >> sh8) & 0xffu) - (int)((pyb >> sh8) & 0xffu)); if (my == 2) giy = __fmul_rn(giy, 2.0f); }
-                sm[c] = __fmul_rn(wgt, (float)((pc >> sh8) & 0xffu));
-                sm[3 + c] = __fmul_rn(wgt, __fmul_rn(gix, rx));
-                sm[6 + c] = __fmul_rn(wgt, __fmul_rn(giy, ry));
-            }
-            sm[9] = wgt;
-        }
-        __syncwarp();
+        BSTAT(2);
         // lanes 0..9 each accumulate one quantity in tap order: Ia[3], Jx[3], Jy[3], s
         // (adding +0 for an absent tap leaves the accumulator bit-identical: it is never -0)
         float acc = lane == 9 ? 1.0e-20f : 0.f;
@@ -570,6 +527,7 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
                 acc = sub ? __fsub_rn(acc, tv) : __fadd_rn(acc, tv);
             }
         }
+        BSTAT(3);
         const float s = __shfl_sync(0xffffffffu, acc, 9);
         const float jx = __shfl_sync(0xffffffffu, acc, min(lane + 3, 31));
         const float jy = __shfl_sync(0xffffffffu, acc, min(lane + 6, 31));
@@ -583,10 +541,10 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
             const float jn = __fadd_rn(__fmul_rn(jx, jx), __fmul_rn(jy, jy));
             bool decided = false;
             if (s > 1.0e-6f && jn > 1.0e-12f && jn < 1.0e30f && fabsf(acc) < 256.0f * s) {
-                float rs, rq;
+                float rs, rq2;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(jn));
-                const float approx = __fadd_rn(__fadd_rn(__fmul_rn(acc, rs), __fmul_rn(__fadd_rn(jx, jy), rq)), 0.5f);
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq2) : "f"(jn));
+                const float approx = __fadd_rn(__fadd_rn(__fmul_rn(acc, rs), __fmul_rn(__fadd_rn(jx, jy), rq2)), 0.5f);
                 const float fl = floorf(approx), fr = __fsub_rn(approx, fl);      // rint(v) = floor(v + 0.5) away from the ties
                 if (fabsf(__fsub_rn(fr, 0.5f)) > 2.0e-3f) {
                     outc = min(max((int)fl + (fr > 0.5f ? 1 : 0), 0), 255);
@@ -604,26 +562,56 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const unsigned
         }
         const unsigned c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
                        c2 = __shfl_sync(0xffffffffu, outc, 2);
-        if (lane == 0) {
-            const unsigned nv = (w.img[MWI(y, x)] & 0x7f000000u) | MARCH_FINAL | c0 | (c1 << 8) | (c2 << 16);
-            *(volatile unsigned long long*)&sh.u.ring[j & (MARCH_RING - 1)] = ((unsigned long long)nv << 32) | (unsigned long long)(j + 1u);
-            *reinterpret_cast<volatile unsigned*>(&V.img[p]) = nv;
-            const unsigned e = *(volatile unsigned*)&sh.wtab[j & (MARCH_RING - 1)];
-            if ((e >> 6) == j + 1u && atomicCAS(&sh.wtab[j & (MARCH_RING - 1)], e, 0u) == e) mbar_arrive(&sh.wbar[e & 63u]);
-#ifdef VSC_TELEA_STATS
-            bt_prev = clock64();
-            atomicAdd(&sh.b_pro, (unsigned long long)(bt1 - bt0)); atomicAdd(&sh.b_wait, (unsigned long long)(bt2 - bt1));
-            atomicAdd(&sh.b_comp, (unsigned long long)(bt_prev - bt2)); atomicAdd(&sh.b_npend, anyp ? 1ull : 0ull);
-            atomicAdd(&sh.b_spins, (unsigned long long)spins); atomicAdd(&sh.b_glob, (unsigned long long)nglob);
-#endif
-        }
-#ifdef VSC_TELEA_STATS
-        bt_prev = __shfl_sync(0xffffffffu, bt_prev, 0);
-#endif
-        __syncwarp();
+        const unsigned nv = (w.img[MWI(y, x)] & 0xff000000u) | c0 | (c1 << 8) | (c2 << 16);
+        BSTAT(4);
 #undef MWI
+        if (lane == 0) {
+            __stcg(reinterpret_cast<unsigned*>(&V.img[p]), nv);
+            __threadfence_block();             // the colour is on its way to L2 before anybody can see a counter drop
+        }
+        __syncwarp();
+        // ---- release the later hole pixels of the window
+        unsigned ready[3];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            ready[r] = MARCH_NONE;
+            const unsigned o = po[r];
+            if (o != MARCH_NONE && o > i) {
+                unsigned left;
+                if (small) {
+                    const unsigned sh8 = 8u * (o & 3u);
+                    const unsigned old = atomicSub(reinterpret_cast<unsigned*>(scnt) + (o >> 2), 1u << sh8);
+                    left = ((old >> sh8) & 0xffu) - 1u;
+                } else left = atomicSub(&gcnt[o], 1u) - 1u;
+                if (left == 0u) { ready[r] = o; any = true; }
+            }
+        }
+        BSTAT(5);
+        // the lowest ready pixel continues on this warp, the others are published
+        unsigned mine = min(ready[0], min(ready[1], ready[2]));
+        mine = __reduce_min_sync(0xffffffffu, mine);
+        if (any) {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (ready[r] != MARCH_NONE && ready[r] != mine) {
+                    const int t = atomicAdd(&sh.rq_tail, 1);
+                    *reinterpret_cast<volatile unsigned*>(&rq[t]) = ready[r];
+                }
+        }
+        if (lane == 0) atomicAdd(&sh.ndone, 1);
+        next = mine; prevp = p; prevc = nv;
+        __syncwarp();
+        BSTAT(6);
+#ifdef VSC_TELEA_STATS
+        if (lane == 0) {
+            atomicAdd(&sh.b_n, 1ull); if (mine != MARCH_NONE) atomicAdd(&sh.b_cont, 1ull);
+            for (int k = 0; k < 6; k++) atomicAdd(&sh.b_ph[k], (unsigned long long)(bts[k + 1] - bts[k]));
+            atomicAdd(&sh.b_ph[6], (unsigned long long)(bts[0] - bt_end));
+            bt_end = bts[6];
+        }
+#endif
     }
-    if (lane == 0) sh.wpar[wid] = par;
     __syncthreads();
 }
 
@@ -635,7 +623,6 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
     const int tid = threadIdx.x, nt = NW * 32, lane = tid & 31, wid = tid >> 5;
     if (tid < 32) { sh.tp.dk[tid] = c_taps.dk[tid]; sh.tp.dl[tid] = c_taps.dl[tid]; sh.tp.dst[tid] = c_taps.dst[tid]; }
     if (tid == 0) sh.flag = 0;
-    if (tid < NW) { mbar_init(&sh.wbar[tid]); sh.wpar[tid] = 0u; }
     const int v = blockIdx.x;       // view-major launch order: the first CTAs to start take each view's biggest cluster
     const TeleaView& V = a.v[v];
     const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
@@ -663,7 +650,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
 #ifdef VSC_TELEA_STATS
         long long ck[5];
         if (tid == 0) { sh.st_gens = sh.st_sweeps = 0; sh.st_sort = sh.st_claim = sh.st_sweep = sh.st_push = 0; ck[0] = clock64();
-                        sh.b_pro = sh.b_wait = sh.b_comp = sh.b_npend = sh.b_spins = sh.b_glob = sh.b_claim = 0; }
+                        for (int k = 0; k < 7; k++) sh.b_ph[k] = 0; sh.b_n = sh.b_cont = 0; }
 #endif
         __syncthreads();
         // the band (initial queue of both sweeps): collect, then order by raster position
@@ -717,7 +704,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
         }
         __syncthreads();
         MSTAT(ck[3] = clock64());
-        march_colour<NW>(V, sh, sc.seq, ntask, Hs, Ws);
+        march_colour<NW>(V, sh, sc, ntask, Hs, Ws);
 #ifdef VSC_TELEA_STATS
         if (tid == 0 && a.stats) {
             ck[4] = clock64();
@@ -729,9 +716,10 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) telea_march_kernel(
             atomicAdd(&st[6], (unsigned long long)ntask);
             if (tot > st[8]) {      // the slowest cluster (racy, good enough for a profile)
                 st[8] = tot; st[9] = ck[1] - ck[0]; st[10] = ck[2] - ck[1]; st[11] = ck[3] - ck[2]; st[12] = ck[4] - ck[3];
-                st[13] = ntask; st[14] = nband; st[15] = sh.st_gens; st[16] = sh.ns; st[17] = sh.st_sweeps;
+                st[13] = ntask; st[14] = nband; st[15] = sh.st_gens; st[16] = 0; st[17] = sh.st_sweeps;
                 st[18] = sh.st_sort; st[19] = sh.st_claim; st[20] = sh.st_sweep; st[21] = sh.st_push;
-                st[22] = sh.b_pro; st[23] = sh.b_wait; st[24] = sh.b_comp; st[25] = sh.b_npend; st[26] = sh.b_spins; st[27] = sh.b_glob; st[28] = sh.b_claim;
+                for (int k = 0; k < 7; k++) st[22 + k] = sh.b_ph[k];
+                st[29] = sh.b_n; st[30] = sh.b_cont;
             }
         }
 #endif

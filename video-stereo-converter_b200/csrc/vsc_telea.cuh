@@ -12,14 +12,9 @@
 //   2. tile CCL kernels       union-find connected components over occupied 8x8 tiles; holes in
 //                             different components are >= 15 px apart (> 2*range+2 = 8, the analytic
 //                             independence bound), so components can be marched independently
-//   3. telea_cluster_kernel   one CTA per cluster (persistent CTAs pull clusters, big ones first) runs the
-//                             sequential algorithm as an ordered task dataflow (outer ring FMM, then the
-//                             inpainting FMM); the 28 window taps of a pixel are evaluated one per lane and
-//                             accumulated in the reference's raster order
-// The priority queue (sorted list with FIFO ties in OpenCV) is realised as generations: all queued
-// entries with T in [Tmin, Tmin+0.7) are extracted, sorted by (T, push order) and popped in order;
-// anything pushed meanwhile has T >= popped T + 1/sqrt(2) and therefore belongs to a later
-// generation, so the pop order is identical to the reference's.
+//   3. telea_march_kernel     (vsc_march.cuh) one CTA per cluster, persistent CTAs pull clusters, big ones first:
+//                             arrival times and computation order in bulk-synchronous generations, then the colours
+//                             as a dataflow over that order
 // Clusters with no hole pixel inside the kept (convergence-cropped) column window are skipped:
 // their pixels are never read by the back end.
 #pragma once
@@ -49,9 +44,9 @@ struct TeleaView {
     // clusters
     int* cl_qoff;  int* cl_toff;  int* cl_ntiles;  int* cl_size;  int* cl_fill;
     int* tile_list;            // [ntiles_active]
-    unsigned long long* qkey[3];   // two ping-pong pools + the current generation
+    unsigned long long* qkey[3];   // march scratch: 6 + 3 arrays of qcap 32-bit words (see telea_march_kernel)
     unsigned* qidx[3];
-    unsigned* pstate;          // [Hs][Ws] order word per pixel for the dataflow (which pop / task owns it, see march)
+    unsigned* pstate;          // [Hs][Ws] order word per pixel: position in the reference's computation order (see march)
     int qcap;
     FrameScalars* fs;          // per-frame counters of the frame this view belongs to
     int vi;                    // 0 = left, 1 = right eye within that frame
@@ -286,18 +281,7 @@ __global__ void telea_cluster_fill_kernel(const __grid_constant__ TeleaArgs a) {
 struct TapConst { signed char dk[32]; signed char dl[32]; float dst[32]; };
 __constant__ TapConst c_taps;   // 28 taps of the radius-3 disc in k-major raster order (centre excluded)
 
-// Per-warp shared-memory window around the pixel being popped.  Every access of one pop (fast-marching
-// solve + Telea weights + gradients) stays within 5 pixels of the popped position, so the window is
-// loaded once per pop with independent, coalesced-by-row loads (one memory round trip) and all the
-// dependent arithmetic then runs out of shared memory; results are written through to global memory.
-constexpr int WIN_R = 5, WIN_D = 2 * WIN_R + 1, WIN_S = WIN_D + 1;
-struct TapTable { int dk[32]; int dl[32]; float dst[32]; };
-struct WarpWin {
-    unsigned char st[WIN_D * WIN_S];
-    float tt[WIN_D * WIN_D];
-    unsigned img[WIN_D * WIN_D];
-    float taps[28 * 10];
-};
+struct TapTable { int dk[32]; int dl[32]; float dst[32]; };    // shared-memory copy of c_taps (constant memory would serialise per lane)
 
 // FastMarching_solve of OpenCV's inpaint.cpp: the arrival time of a pixel from two of its 4-neighbours
 // (t1 / t2 their arrival times, in1 / in2 whether they are still INSIDE, i.e. unknown)
@@ -314,648 +298,6 @@ __device__ __forceinline__ float fmm_solve(float t1, float t2, bool in1, bool in
     } else if (!in2) sol = __dadd_rn(1.0, a22);
     else sol = __dadd_rn(1.0, m12);
     return (float)sol;
-}
-
-struct Marcher {
-    const TeleaView& V;
-    int Hs, Ws;
-    int lane;
-    WarpWin* w;
-    const TapTable* tp;   // shared-memory copy of the tap constants (constant memory would serialise per lane)
-    int wy0, wx0;   // image coordinates of window element (0,0)
-    __device__ __forceinline__ bool inb(int y, int x) const { return y >= 0 && y < Hs && x >= 0 && x < Ws; }
-    // (re)load the window of radius r <= WIN_R centred on (yc, xc); pixels outside the image read as the
-    // 1-pixel KNOWN frame (t = 1e6) that cv2.inpaint adds around the image
-    template <int R, bool WITH_IMG> __device__ __forceinline__ void load(int yc, int xc) {
-        wy0 = yc - WIN_R; wx0 = xc - WIN_R;
-        constexpr int D = 2 * R + 1, NIT = (D * D + 31) / 32;
-        unsigned char sv[NIT]; float tv[NIT]; unsigned iv[NIT];
-#pragma unroll
-        for (int it = 0; it < NIT; it++) {       // issue every load before the first use
-            const int idx = lane + 32 * it;
-            const int ly = idx / D + (WIN_R - R), lx = idx % D + (WIN_R - R);
-            const int y = wy0 + ly, x = wx0 + lx;
-            sv[it] = 0; tv[it] = 1.0e6f; iv[it] = 0;
-            if (idx < D * D && inb(y, x)) {
-                const size_t p = (size_t)y * Ws + x;
-                sv[it] = V.st[p]; tv[it] = V.tt[p];
-                if (WITH_IMG) iv[it] = *reinterpret_cast<const unsigned*>(&V.img[p]);
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < NIT; it++) {
-            const int idx = lane + 32 * it;
-            if (idx < D * D) {
-                const int ly = idx / D + (WIN_R - R), lx = idx % D + (WIN_R - R);
-                w->st[ly * WIN_S + lx] = sv[it]; w->tt[ly * WIN_D + lx] = tv[it];
-                if (WITH_IMG) w->img[ly * WIN_D + lx] = iv[it];
-            }
-        }
-        __syncwarp();
-    }
-    __device__ __forceinline__ unsigned char S(int y, int x) const { return w->st[(y - wy0) * WIN_S + (x - wx0)]; }
-    __device__ __forceinline__ float Traw(int y, int x) const { return w->tt[(y - wy0) * WIN_D + (x - wx0)]; }
-    template <bool OUTER> __device__ __forceinline__ bool inside(int y, int x) const {
-        const unsigned char s = S(y, x);
-        return OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE);
-    }
-    // T as the inpainting pass sees it: the outer pass' distances are negated (icvCalcFMM negate=true)
-    __device__ __forceinline__ float T_main(int y, int x) const {
-        const float t = Traw(y, x);
-        return ((S(y, x) & O_MASK) == O_CHANGE) ? -t : t;
-    }
-    template <bool OUTER> __device__ __forceinline__ float solve(int y1, int x1, int y2, int x2) const {
-        return fmm_solve(OUTER ? Traw(y1, x1) : T_main(y1, x1), OUTER ? Traw(y2, x2) : T_main(y2, x2),
-                         inside<OUTER>(y1, x1), inside<OUTER>(y2, x2));
-    }
-    // the four corner solves run on lanes 0..3; every lane returns the minimum
-    template <bool OUTER> __device__ __forceinline__ float min4(int y, int x) const {
-        const int l = lane & 3;
-        const float s = solve<OUTER>(y + ((l & 1) ? 1 : -1), x, y, x + ((l & 2) ? 1 : -1));
-        const float a = fminf(s, __shfl_xor_sync(0xffffffffu, s, 1));
-        return fminf(a, __shfl_xor_sync(0xffffffffu, a, 2));
-    }
-    __device__ __forceinline__ int pix(int y, int x, int c) const { return (w->img[(y - wy0) * WIN_D + (x - wx0)] >> (8 * c)) & 0xff; }
-    // write-through updates by lane 0
-    __device__ __forceinline__ void set_T(int y, int x, float t) const {
-        V.tt[(size_t)y * Ws + x] = t; w->tt[(y - wy0) * WIN_D + (x - wx0)] = t;
-    }
-    __device__ __forceinline__ void set_S(int y, int x, unsigned char s) const {
-        V.st[(size_t)y * Ws + x] = s; w->st[(y - wy0) * WIN_S + (x - wx0)] = s;
-    }
-    // icvTeleaInpaintFMM body for one pixel (y,x) whose T was just set to `dist`; warp-cooperative
-    __device__ void inpaint(int y, int x, float dist) const {
-        float* sm = w->taps;
-        // gradT (warp-uniform)
-        float gtx, gty;
-        {
-            const bool r = !inside<false>(y, x + 1), l = !inside<false>(y, x - 1);
-            const bool d = !inside<false>(y + 1, x), u = !inside<false>(y - 1, x);
-            if (r) gtx = l ? __fmul_rn(__fsub_rn(T_main(y, x + 1), T_main(y, x - 1)), 0.5f) : __fsub_rn(T_main(y, x + 1), dist);
-            else gtx = l ? __fsub_rn(dist, T_main(y, x - 1)) : 0.f;
-            if (d) gty = u ? __fmul_rn(__fsub_rn(T_main(y + 1, x), T_main(y - 1, x)), 0.5f) : __fsub_rn(T_main(y + 1, x), dist);
-            else gty = u ? __fsub_rn(dist, T_main(y - 1, x)) : 0.f;
-        }
-        bool valid = false;
-        float term[10];
-        if (lane < 28) {
-            const int dk = tp->dk[lane], dl = tp->dl[lane];
-            const int ky = y + dk, kx = x + dl;
-            if (inb(ky, kx) && !inside<false>(ky, kx)) {
-                valid = true;
-                const float ry = (float)(-dk), rx = (float)(-dl);
-                const float dst = tp->dst[lane];
-                const float lev = (float)__ddiv_rn(1.0, __dadd_rn(1.0, fabs((double)__fsub_rn(T_main(ky, kx), dist))));
-                float dir = __fadd_rn(__fmul_rn(rx, gtx), __fmul_rn(ry, gty));
-                if (fabs((double)dir) <= 0.01) dir = 0.000001f;
-                const float wgt = fabsf(__fmul_rn(__fmul_rn(dst, lev), dir));
-                const bool fr = !inside<false>(ky, kx + 1), fl = !inside<false>(ky, kx - 1);
-                const bool fd = !inside<false>(ky + 1, kx), fu = !inside<false>(ky - 1, kx);
-                const int km = ky + (ky == 0), kp = ky - (ky == Hs - 1);
-                const int lm = kx + (kx == 0), lp = kx - (kx == Ws - 1);
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    float gix, giy;
-                    if (fr) gix = fl ? __fmul_rn((float)(pix(km, lp + 1, c) - pix(km, lm - 1, c)), 2.0f)
-                                     : (float)(pix(km, lp + 1, c) - pix(km, lm, c));
-                    else gix = fl ? (float)(pix(km, lp, c) - pix(km, lm - 1, c)) : 0.f;
-                    if (fd) giy = fu ? __fmul_rn((float)(pix(kp + 1, lm, c) - pix(km - 1, lm, c)), 2.0f)
-                                     : (float)(pix(kp + 1, lm, c) - pix(km, lm, c));
-                    else giy = fu ? (float)(pix(kp, lm, c) - pix(km - 1, lm, c)) : 0.f;
-                    term[c] = __fmul_rn(wgt, (float)pix(ky, kx, c));
-                    term[3 + c] = __fmul_rn(wgt, __fmul_rn(gix, rx));
-                    term[6 + c] = __fmul_rn(wgt, __fmul_rn(giy, ry));
-                }
-                term[9] = wgt;
-            }
-        }
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-#pragma unroll
-            for (int q = 0; q < 10; q++) sm[lane * 10 + q] = term[q];
-        }
-        __syncwarp();
-        // lanes 0..9 each accumulate one quantity in tap (raster) order: Ia[3], Jx[3], Jy[3], s
-        // (adding +0 for an absent tap leaves the accumulator bit-identical: it is never -0)
-        float acc = lane == 9 ? 1.0e-20f : 0.f;
-        {
-            const int col = lane < 10 ? lane : 0;
-            const bool sub = lane >= 3 && lane < 9;
-            float t[28];
-#pragma unroll
-            for (int L = 0; L < 28; L++) t[L] = sm[L * 10 + col];
-#pragma unroll
-            for (int L = 0; L < 28; L++) {
-                const float tv = ((vm >> L) & 1u) ? t[L] : 0.f;
-                acc = sub ? __fsub_rn(acc, tv) : __fadd_rn(acc, tv);
-            }
-        }
-        const float s = __shfl_sync(0xffffffffu, acc, 9);
-        const float jx = __shfl_sync(0xffffffffu, acc, min(lane + 3, 31));
-        const float jy = __shfl_sync(0xffffffffu, acc, min(lane + 6, 31));
-        int outc = 0;
-        if (lane < 3) {
-            const float ia_s = __fdiv_rn(acc, s);
-            const float jsum = __fadd_rn(jx, jy);
-            const float jn = __fadd_rn(__fmul_rn(jx, jx), __fmul_rn(jy, jy));
-            const double den = __dadd_rn(sqrt((double)jn), (double)1.0e-20f);
-            const double val = __dadd_rn(__dadd_rn((double)ia_s, __ddiv_rn((double)jsum, den)), (double)0.5f);
-            const float sat = (float)val;
-            outc = min(max(__float2int_rn(sat), 0), 255);
-        }
-        const unsigned c0 = __shfl_sync(0xffffffffu, outc, 0), c1 = __shfl_sync(0xffffffffu, outc, 1),
-                       c2 = __shfl_sync(0xffffffffu, outc, 2);
-        __syncwarp();
-        if (lane == 0) {
-            const int li = (y - wy0) * WIN_D + (x - wx0);
-            const unsigned nv = (w->img[li] & 0xff000000u) | c0 | (c1 << 8) | (c2 << 16);
-            w->img[li] = nv;
-            V.img[(size_t)y * Ws + x] = make_uchar4((unsigned char)c0, (unsigned char)c1, (unsigned char)c2, (unsigned char)(nv >> 24));
-        }
-    }
-};
-
-// ---- CTA-wide helpers --------------------------------------------------------------------------------
-__device__ __forceinline__ void cmpswap(unsigned long long* key, unsigned* idx, int i, int p) {
-    const unsigned long long a = key[i], b = key[p];
-    if (a > b) {
-        key[i] = b; key[p] = a;
-        const unsigned t = idx[i]; idx[i] = idx[p]; idx[p] = t;
-    }
-}
-// CTA-wide bitonic sort of n (key,idx) pairs in global memory, ascending by key.  All compare-exchanges
-// are ascending (the "flip" formulation), so the virtual +inf padding above n never has to move and pairs
-// whose partner is >= n are simply skipped.
-__device__ void block_sort(unsigned long long* key, unsigned* idx, int n) {
-    if (n <= 1) return;
-    int N = 1;
-    while (N < n) N <<= 1;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int i = tid; i < n; i += nt) {
-            const int p = i ^ (k - 1);
-            if (p > i && p < n) cmpswap(key, idx, i, p);
-        }
-        __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += nt) {
-                const int p = i ^ j;
-                if (p > i && p < n) cmpswap(key, idx, i, p);
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// Warps per march CTA (template parameter NW of the kernel).  Measured on a B200 at 1080p: with many frames in
-// flight 8 warps give the best throughput (4 / 6 / 8 / 12 warps: 572 / 585 / 604 / 559 frames/s); a single frame
-// alone finishes sooner with 16 (22 ms vs 35 ms), which is what a context with one slot gets.
-constexpr int TELEA_WARPS_THROUGHPUT = 8, TELEA_WARPS_LATENCY = 16;
-#ifndef VSC_OUTER_LANES
-#define VSC_OUTER_LANES 1     // outer-ring distance pass: one task per lane (0 = one task per warp, the first implementation)
-#endif
-// Two compute tasks of one generation whose pixels are closer than this (Chebyshev) run in queue order;
-// farther apart they commute.  Inpainting a pixel reads flags / T / colours within 4 of it and writes only
-// the pixel itself -> 4.  An outer-ring distance reads the 4-neighbours and writes the pixel -> 1.
-constexpr int TELEA_DC_MAIN = 4, TELEA_DC_OUTER = 1;
-
-constexpr int TELEA_RING = 1024;      // completion ring entries (> tasks in flight: 32 per warp in the outer pass)
-constexpr int TELEA_MAXDEP = 32;      // compact dependency list per warp (one entry per lane); more (rare): per-lane polling
-template <int NW> struct MarchShared {
-    int npool, npool2, ncur, ntask, next_t, done_t, gbase, scan_total, need_left;
-    unsigned tmin;
-    unsigned tbase;                    // CTA-monotonic index of the current generation's first task
-    int ci;
-    int wsum[NW];
-    unsigned ring[TELEA_RING];         // ring[J % RING] = J + 1 once task J has finished (monotonic per entry)
-    unsigned wdep[NW][TELEA_MAXDEP];
-    WarpWin win[NW];
-#ifdef VSC_TELEA_STATS
-    unsigned long long c_wait, c_pop, c_sort, c_part, c_total, n_pops, n_pix, n_gen, n_polls, c_load, c_inp, c_rel, c_min4;
-#endif
-};
-
-// pstate word per pixel: (index << 2) | kind
-//   pop  of the current generation : (G << 2) | 1      G = global pop index (rank in sorted order)
-//   compute task                   : (J << 2) | 2      J = CTA-monotonic task index = order in which a sequential run
-//                                                      performs the tasks (also the FIFO tie-break of the queue)
-//   never touched                  : 0xffffffff
-// Whether task J has finished is NOT recorded here but in the CTA's shared-memory completion ring (MarchShared::ring):
-// a waiting warp polls shared memory, not global memory.
-__device__ __forceinline__ bool ps_is_pop(unsigned v) { return (v & 3u) == 1u; }
-__device__ __forceinline__ bool ps_is_task(unsigned v) { return (v & 3u) == 2u; }
-
-
-#if VSC_OUTER_LANES
-// Outer-ring pass: a distance task only reads the arrival times and flags of its 4-neighbours, so a LANE runs
-// a task: a warp claims 32 consecutive tasks, every lane collects the earlier tasks of the generation among
-// its 4 neighbours, and the warp iterates until all its lanes have run (the earliest unfinished task of the
-// CTA never waits, so this terminates).  Same order, same arithmetic, ~100x fewer warp instructions per task.
-// (Its own function, not inlined: the main pass keeps its register allocation.)
-template <int NW>
-__device__ __noinline__ void outer_lane_dataflow(const TeleaView& V, MarchShared<NW>& sh, int Hs, int Ws, int ntask, int carry,
-                                                 const unsigned* next_i, unsigned long long* next_k) {
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sh.next_t, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= ntask) break;
-        const int j = base + lane;
-        const bool active = j < ntask;
-        const unsigned tbase = sh.tbase, J = tbase + (unsigned)j;
-        unsigned pn = 0;
-        int y = 0, x = 0;
-        // a task reads (and is read by) its 4-neighbours only: those with an earlier task of this generation are
-        // its dependencies (q: 0 up, 1 down, 2 left, 3 right)
-        unsigned dep[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) dep[q] = 0xffffffffu;
-        if (active) {
-            pn = next_i[carry + j];
-            y = (int)(pn / (unsigned)Ws); x = (int)(pn - (unsigned)y * (unsigned)Ws);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int yy = y + (q == 0 ? -1 : (q == 1 ? 1 : 0)), xx = x + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                if ((yy >= 0 && yy < Hs && xx >= 0 && xx < Ws)) {
-                    const unsigned v = V.pstate[(size_t)yy * Ws + xx];      // stable during the dataflow
-                    if (ps_is_task(v) && (v >> 2) >= tbase && (v >> 2) < J) dep[q] = v >> 2;
-                }
-            }
-        }
-        bool done = !active;
-        while (true) {
-            bool ready = !done;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (dep[q] != 0xffffffffu) {
-                    if (*(volatile unsigned*)&sh.ring[dep[q] & (TELEA_RING - 1)] >= dep[q] + 1u) dep[q] = 0xffffffffu;
-                    else ready = false;
-                }
-            if (ready) {
-                __threadfence_block();
-                // arrival times / flags of the 4-neighbours; outside the image: the KNOWN frame with T = 1e6
-                float tn[4]; bool in_[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int yy = y + (q == 0 ? -1 : (q == 1 ? 1 : 0)), xx = x + (q == 2 ? -1 : (q == 3 ? 1 : 0));
-                    tn[q] = 1.0e6f; in_[q] = false;
-                    if ((yy >= 0 && yy < Hs && xx >= 0 && xx < Ws)) {
-                        const size_t p = (size_t)yy * Ws + xx;
-                        tn[q] = V.tt[p];       // ordered after the ring reads by the fence above (CTA scope: same SM, same L1)
-                        in_[q] = (V.st[p] & O_MASK) == O_INSIDE;
-                    }
-                }
-                // the four corner solves in min4's pairing: (up,left) (down,left) | (up,right) (down,right)
-                const float s0 = fmm_solve(tn[0], tn[2], in_[0], in_[2]), s1 = fmm_solve(tn[1], tn[2], in_[1], in_[2]);
-                const float s2 = fmm_solve(tn[0], tn[3], in_[0], in_[3]), s3 = fmm_solve(tn[1], tn[3], in_[1], in_[3]);
-                const float dist = fminf(fminf(s0, s1), fminf(s2, s3));
-                V.tt[pn] = dist;
-                V.st[pn] = (unsigned char)((V.st[pn] & ~O_MASK) | O_BAND);
-                next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)J;
-                volatile unsigned* slot = &sh.ring[J & (TELEA_RING - 1)];
-                while (J >= (unsigned)TELEA_RING && *slot < J - (unsigned)TELEA_RING + 1u) __nanosleep(20);
-                __threadfence_block();
-                *slot = J + 1u;
-                done = true;
-            }
-            const unsigned left = __ballot_sync(0xffffffffu, !done);
-            if (!left) break;
-            if (!__any_sync(0xffffffffu, ready)) __nanosleep(40);     // nobody moved: wait for another warp
-        }
-#ifdef VSC_TELEA_STATS
-        if (lane == 0) atomicAdd(&sh.n_pix, (unsigned long long)min(32, ntask - base));
-#endif
-    }
-}
-#endif
-
-// One fast-marching pass over one cluster, executed by a whole CTA.
-//  * the queue is processed in generations (see file header); each generation is sorted CTA-wide.
-//  * popping an entry computes those 4-neighbours that are still INSIDE; each such pixel is computed by the
-//    FIRST popped neighbour (its owner).  Ownership only depends on the sorted order, so the list of compute
-//    tasks of a generation, ordered by (owner rank, neighbour index) = the order in which a sequential run
-//    performs them, is built up front in parallel.
-//  * the tasks then run as a dataflow: warps claim tasks in order and a task starts once every earlier task
-//    of its generation within TELEA_DC_* pixels has finished.  Tasks farther apart commute, so the result is
-//    identical to the sequential order.  The dependencies of a task are read once from pstate (which pixel
-//    belongs to which task), compacted into a short per-warp list, and then polled in the shared-memory
-//    completion ring - a handful of instructions per poll instead of a sweep over global memory.
-//  * the FIFO tie-break of the reference's queue is the task index J, i.e. the sequential push order.
-template <bool OUTER, int NW>
-__device__ void march(Marcher& mc, const TeleaView& V, MarchShared<NW>& sh, int qoff, int ntiles, const int* tiles, int tw,
-                      int keep_x0, int keep_x1, unsigned long long* stats) {
-    unsigned long long* pk[2] = {V.qkey[0] + qoff, V.qkey[1] + qoff};
-    unsigned* pi[2] = {V.qidx[0] + qoff, V.qidx[1] + qoff};
-    unsigned long long* cur_k = V.qkey[2] + qoff;
-    unsigned* cur_i = V.qidx[2] + qoff;
-    const int Ws = mc.Ws, Hs = mc.Hs, lane = mc.lane, wid = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { sh.npool = 0; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.done_t = 0; sh.tmin = 0xffffffffu; if (OUTER) sh.gbase = 1; }
-#ifdef VSC_TELEA_STATS
-    if (tid == 0) { sh.c_wait = sh.c_pop = sh.c_sort = sh.c_part = sh.n_pops = sh.n_pix = sh.n_gen = sh.n_polls = sh.c_load = sh.c_inp = sh.c_rel = sh.c_min4 = 0; }
-    const long long t_start = clock64();
-    long long t_mark;
-#define STAT_MARK() t_mark = clock64()
-#define STAT_ADD(field) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_mark)); } while (0)
-#define STAT_ADD0(field) do { if (tid == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_mark)); } while (0)
-#define STAT_INC(field, n) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(n)); } while (0)
-#define STAT_T0() const long long t_sub = clock64()
-#define STAT_T1(field) do { if (lane == 0) atomicAdd(&sh.field, (unsigned long long)(clock64() - t_sub)); } while (0)
-#else
-#define STAT_MARK()
-#define STAT_ADD(field)
-#define STAT_ADD0(field)
-#define STAT_INC(field, n)
-#define STAT_T0()
-#define STAT_T1(field)
-#endif
-    __syncthreads();
-    // initial queue: the band pixels, T = 0, ordered by raster position (= linear index in the key)
-    for (int ti = wid; ti < ntiles; ti += NW) {
-        const int t = tiles[ti];
-        const int ty = t / tw, tx = t - ty * tw;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int y = ty * TG + (lane >> 3) + 4 * h, x = tx * TG + (lane & 7);
-            bool isb = false;
-            unsigned p = 0;
-            if (y < Hs && x < Ws) { p = (unsigned)y * (unsigned)Ws + (unsigned)x; isb = (V.st[p] & ST_BAND0) != 0; }
-            const unsigned bm = __ballot_sync(0xffffffffu, isb);
-            int base = 0;
-            if (lane == 0 && bm) base = atomicAdd(&sh.npool, __popc(bm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (isb) {
-                const int pos = base + __popc(bm & ((1u << lane) - 1));
-                pk[0][pos] = (unsigned long long)p;
-                pi[0][pos] = p;
-            }
-        }
-    }
-    __syncthreads();
-    int src = 0;
-    while (true) {
-        const int npool = sh.npool;
-        if (npool == 0) break;
-        unsigned long long* pool_k = pk[src]; unsigned* pool_i = pi[src];
-        unsigned long long* next_k = pk[src ^ 1]; unsigned* next_i = pi[src ^ 1];
-        STAT_MARK();
-        // ---- generation = entries with T < Tmin + 0.7 ---------------------------------------------------
-        unsigned tmin = 0xffffffffu;
-        for (int i = tid; i < npool; i += nt) tmin = min(tmin, (unsigned)(pool_k[i] >> 32));
-        tmin = __reduce_min_sync(0xffffffffu, tmin);
-        if (lane == 0) atomicMin(&sh.tmin, tmin);
-        __syncthreads();
-        const float thr = __uint_as_float(sh.tmin) + 0.7f;
-        for (int i = tid; i < npool; i += nt) {
-            const unsigned long long k = pool_k[i];
-            const unsigned p = pool_i[i];
-            if (__uint_as_float((unsigned)(k >> 32)) < thr) {
-                const int pos = atomicAdd(&sh.ncur, 1);
-                cur_k[pos] = k; cur_i[pos] = p;
-            } else {
-                const int pos = atomicAdd(&sh.npool2, 1);
-                next_k[pos] = k; next_i[pos] = p;
-            }
-        }
-        __syncthreads();
-        const int ncur = sh.ncur, gbase = sh.gbase, carry = sh.npool2;
-        STAT_ADD0(c_part);
-        STAT_MARK();
-        block_sort(cur_k, cur_i, ncur);
-        __syncthreads();
-        STAT_ADD0(c_sort);
-        if (tid == 0) { STAT_INC(n_gen, 1); STAT_INC(n_pops, ncur); }
-        STAT_MARK();
-        // ---- mark the pops of this generation (and the outer pass' CHANGE flag, which nothing orders) -------
-        for (int e = tid; e < ncur; e += nt) {
-            const unsigned p = cur_i[e];
-            V.pstate[p] = ((unsigned)(gbase + e) << 2) | 1u;
-            if (OUTER) V.st[p] = (V.st[p] & ~O_MASK) | O_CHANGE;
-        }
-        __syncthreads();
-        // ---- ownership: which INSIDE neighbours does pop e compute?  (mask of q in cur_k[e]) ---------------
-        for (int e0 = 0; e0 < ncur; e0 += nt) {
-            const int e = e0 + tid;
-            unsigned own = 0;
-            if (e < ncur) {
-                const unsigned p = cur_i[e];
-                const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
-                const unsigned G = (unsigned)(gbase + e);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
-                    if (!mc.inb(y, x)) continue;
-                    const unsigned char s = V.st[(size_t)y * Ws + x];
-                    if (!(OUTER ? ((s & O_MASK) == O_INSIDE) : ((s & F_MASK) == F_INSIDE))) continue;
-                    bool first = true;     // no 4-neighbour of (y,x) is popped earlier in this generation
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const int y2 = y + (r == 0 ? -1 : (r == 2 ? 1 : 0)), x2 = x + (r == 1 ? -1 : (r == 3 ? 1 : 0));
-                        if (!mc.inb(y2, x2)) continue;
-                        const unsigned v = V.pstate[(size_t)y2 * Ws + x2];
-                        if (ps_is_pop(v) && (v >> 2) >= (unsigned)gbase && (v >> 2) < G) first = false;
-                    }
-                    if (first) own |= 1u << q;
-                }
-                cur_k[e] = own;
-            }
-            // exclusive scan of popc(own) over the generation, chunk by chunk
-            const int c = __popc(own);
-            int inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            if (lane == 31) sh.wsum[wid] = inc;
-            __syncthreads();
-            int woff = 0;
-            for (int w2 = 0; w2 < wid; w2++) woff += sh.wsum[w2];
-            const int off = sh.ntask + woff + inc - c;
-            if (e < ncur && own) {
-                const unsigned p = cur_i[e];
-                const int yy = (int)(p / (unsigned)Ws), xx = (int)(p - (unsigned)yy * (unsigned)Ws);
-                int j = 0;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (!(own & (1u << q))) continue;
-                    const int y = yy + (q == 0 ? -1 : (q == 2 ? 1 : 0)), x = xx + (q == 1 ? -1 : (q == 3 ? 1 : 0));
-                    const unsigned pn = (unsigned)y * (unsigned)Ws + (unsigned)x;
-                    next_i[carry + off + j] = pn;         // key (T, J) is filled in when the task runs
-                    V.pstate[pn] = ((sh.tbase + (unsigned)(off + j)) << 2) | 2u;
-                    j++;
-                }
-            }
-            __syncthreads();
-            if (tid == nt - 1) sh.ntask = off + c;     // last thread holds the inclusive total of this chunk
-            __syncthreads();
-        }
-        const int ntask = sh.ntask;
-        STAT_ADD0(c_part);
-        // ---- dataflow over the ordered tasks -------------------------------------------------------------
-#if VSC_OUTER_LANES
-        if (OUTER) outer_lane_dataflow<NW>(V, sh, Hs, Ws, ntask, carry, next_i, next_k);
-#endif
-        while (!(VSC_OUTER_LANES && OUTER)) {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&sh.next_t, 1);
-            j = __shfl_sync(0xffffffffu, j, 0);
-            if (j >= ntask) break;
-            const unsigned pn = next_i[carry + j];
-            const unsigned tbase = sh.tbase, J = tbase + (unsigned)j;
-            const int y = (int)(pn / (unsigned)Ws), x = (int)(pn - (unsigned)y * (unsigned)Ws);
-            STAT_MARK();
-            {   // wait for every earlier task of this generation within TELEA_DC
-                constexpr int DC = OUTER ? TELEA_DC_OUTER : TELEA_DC_MAIN;
-                constexpr int D = 2 * DC + 1, NIT = (D * D + 31) / 32;
-                unsigned* wd = sh.wdep[wid];
-                unsigned depr[NIT];
-                int nd = 0;
-#pragma unroll
-                for (int r = 0; r < NIT; r++) {
-                    const int idx = lane + 32 * r;
-                    const int yy = y + idx / D - DC, xx = x + idx % D - DC;
-                    unsigned dep = 0xffffffffu;
-                    if (idx < D * D && mc.inb(yy, xx)) {
-                        const unsigned v = V.pstate[(size_t)yy * Ws + xx];      // stable during the dataflow
-                        if (ps_is_task(v) && (v >> 2) >= tbase && (v >> 2) < J) dep = v >> 2;
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, dep != 0xffffffffu);
-                    const int pos = nd + __popc(bal & ((1u << lane) - 1u));
-                    if (dep != 0xffffffffu && pos < TELEA_MAXDEP) wd[pos] = dep;
-                    nd += __popc(bal);
-                    depr[r] = dep;
-                }
-                __syncwarp();
-                STAT_INC(n_polls, 1);
-                if (nd > 0 && nd <= TELEA_MAXDEP) {
-                    const unsigned mine = lane < nd ? wd[lane] : 0xffffffffu;
-                    const volatile unsigned* slot = &sh.ring[mine & (TELEA_RING - 1)];
-                    bool pend = lane < nd;
-                    while (true) {
-                        if (pend) pend = *slot < mine + 1u;
-                        if (!__any_sync(0xffffffffu, pend)) break;
-                        // Only the oldest unfinished tasks are on the critical path: poll them eagerly; the further a
-                        // claimed task is behind the completion front, the longer it sleeps (waiting warps must not
-                        // steal issue slots from the working ones).
-                        const int behind = j - *(volatile int*)&sh.done_t;
-                        __nanosleep(behind <= 2 ? 40 : min(behind * 200, 4000));
-                        STAT_INC(n_polls, 1);
-                    }
-                    __threadfence_block();
-                } else if (nd > 0) {       // more dependencies than the list holds: every lane polls its own
-                    while (true) {
-                        bool pend = false;
-#pragma unroll
-                        for (int r = 0; r < NIT; r++)
-                            if (depr[r] != 0xffffffffu) {
-                                if (*(volatile unsigned*)&sh.ring[depr[r] & (TELEA_RING - 1)] >= depr[r] + 1u) depr[r] = 0xffffffffu;
-                                else pend = true;
-                            }
-                        if (!__any_sync(0xffffffffu, pend)) break;
-                        __nanosleep(100);
-                    }
-                    __threadfence_block();
-                }
-            }
-            STAT_ADD(c_wait);
-            STAT_MARK();
-            { STAT_T0(); mc.template load<OUTER ? 1 : 4, !OUTER>(y, x); STAT_T1(c_load); }
-            float dist;
-            { STAT_T0(); dist = mc.min4<OUTER>(y, x); STAT_T1(c_min4); }
-            __syncwarp();
-            if (lane == 0) mc.set_T(y, x, dist);
-            __syncwarp();
-            STAT_INC(n_pix, 1);
-#ifndef VSC_EXPERIMENT_NO_INPAINT
-            if (!OUTER) { STAT_T0(); mc.inpaint(y, x, dist); STAT_T1(c_inp); }
-#endif
-            if (lane == 0) {
-                const unsigned char s = mc.S(y, x);
-                mc.set_S(y, x, OUTER ? ((s & ~O_MASK) | O_BAND) : ((s & ~F_MASK) | F_BAND));
-                next_k[carry + j] = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)J;
-                if (!OUTER && x >= keep_x0 && x < keep_x1) atomicSub(&sh.need_left, 1);
-            }
-            __syncwarp();
-            {   // publish: results first, then the ring entry.  An entry is only overwritten once its previous occupant
-                // (J - RING, claimed long ago) has finished, so "ring[J % RING] >= J + 1" always means "J is done".
-                STAT_T0();
-                if (lane == 0) {
-                    volatile unsigned* slot = &sh.ring[J & (TELEA_RING - 1)];
-                    while (J >= (unsigned)TELEA_RING && *slot < J - (unsigned)TELEA_RING + 1u) __nanosleep(20);
-                    __threadfence_block();
-                    *slot = J + 1u;
-                    atomicAdd(&sh.done_t, 1);
-                }
-                __syncwarp();
-                STAT_T1(c_rel);
-            }
-            STAT_ADD(c_pop);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            sh.gbase = gbase + ncur; sh.npool = carry + ntask; sh.npool2 = 0; sh.ncur = 0; sh.ntask = 0; sh.next_t = 0; sh.done_t = 0; sh.tmin = 0xffffffffu;
-            sh.tbase += (unsigned)ntask;
-        }
-        src ^= 1;
-        __syncthreads();
-        // Everything still queued has a larger T than every pixel computed so far and can therefore not influence
-        // them; once all hole pixels inside the kept window are filled, the rest of the cluster is never read.
-        if (!OUTER && sh.need_left <= 0) break;
-    }
-#ifdef VSC_TELEA_STATS
-    if (tid == 0 && stats) {
-        const unsigned long long tot = (unsigned long long)(clock64() - t_start);
-        atomicAdd(&stats[0], sh.c_wait); atomicAdd(&stats[1], sh.c_pop); atomicAdd(&stats[2], sh.c_sort);
-        atomicAdd(&stats[3], sh.c_part); atomicAdd(&stats[4], tot); atomicAdd(&stats[5], sh.n_pops);
-        atomicAdd(&stats[6], sh.n_pix); atomicAdd(&stats[7], sh.n_gen); atomicAdd(&stats[8], sh.n_polls);
-        atomicAdd(&stats[9], 1ull);
-        if (tot > stats[10]) {   // record of the slowest cluster (racy but good enough for a profile)
-            stats[10] = tot; stats[11] = sh.n_pops; stats[12] = sh.c_load; stats[13] = sh.c_min4; stats[14] = sh.c_inp; stats[15] = sh.c_rel;
-        }
-    }
-#endif
-}
-
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1024 / (NW * 32)) telea_cluster_kernel(const __grid_constant__ TeleaArgs a) {
-    __shared__ MarchShared<NW> sh;
-    __shared__ TapTable tp;
-    if (threadIdx.x < 32) { tp.dk[threadIdx.x] = c_taps.dk[threadIdx.x]; tp.dl[threadIdx.x] = c_taps.dl[threadIdx.x]; tp.dst[threadIdx.x] = c_taps.dst[threadIdx.x]; }
-    for (int i = threadIdx.x; i < TELEA_RING; i += blockDim.x) sh.ring[i] = 0u;
-    if (threadIdx.x == 0) sh.tbase = 0u;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int v = blockIdx.x;       // view-major launch order: the first CTAs to start take each view's biggest cluster
-    const TeleaView& V = a.v[v];
-    const int nbig = V.fs->nbig[V.vi], ncl = nbig + V.fs->nsmall[V.vi];
-    if (V.fs->qbump[V.vi] > V.qcap) {   // scratch too small: report and leave the frame to the host retry
-        if (threadIdx.x == 0 && blockIdx.y == 0) atomicMax(&V.fs->overflow, V.fs->qbump[V.vi]);
-        return;
-    }
-    Marcher mc{V, a.Hs, a.Ws, lane, &sh.win[threadIdx.x >> 5], &tp, 0, 0};
-    const int cap = a.tw * a.th;
-    while (true) {
-        if (threadIdx.x == 0) sh.ci = atomicAdd(&V.fs->next[V.vi], 1);
-        __syncthreads();
-        const int i = sh.ci;
-        if (i >= ncl) break;
-        const int ci = i < nbig ? i : cap - 1 - (i - nbig);     // big clusters are queued first
-        const int qoff = V.cl_qoff[ci], ntiles = V.cl_ntiles[ci];
-        const int* tiles = V.tile_list + V.cl_toff[ci];
-        if (threadIdx.x == 0) sh.need_left = V.cl_size[ci];
-#ifdef VSC_EXPERIMENT_SLEEP_MARCH
-        {   // experiment: hold the CTA's resources for about as long as the march would take, without issuing work
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            const unsigned long long dur = (unsigned long long)V.cl_size[ci] * VSC_EXPERIMENT_SLEEP_MARCH;
-            do { __nanosleep(100000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < dur);
-            __syncthreads();
-            continue;
-        }
-#endif
-        march<true, NW>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 0) * 16 : nullptr);
-        __syncthreads();
-        march<false, NW>(mc, V, sh, qoff, ntiles, tiles, a.tw, V.keep_x0, V.keep_x1, a.stats ? a.stats + ((v & 1) * 2 + 1) * 16 : nullptr);
-        __syncthreads();
-    }
 }
 
 }  // namespace vsc
