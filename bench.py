@@ -4,23 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path over one batch of `--batch` synthetic 1080p frames
-(config "1080p 300-frame synthetic clip, default config.json stereo params", BASELINE.json
-configs[1]); frames are independent, so with N GPUs every rank processes its own batch (frame-range
-sharding, no collective; "scaling": "weak") and the reported value is total frames / max-over-ranks
-device time.  The K timed steps are K consecutive batches of ONE continuous clip: they overlap in the
-slot pipeline the way consecutive seconds of a video do, and the timed region is bracketed by a
-barrier + full drain + synchronize on both sides (pipeline fill and drain are inside it).
+Headline workload (BASELINE.json configs[1]): a 1080p synthetic clip, uint8 depth, default config.json stereo
+parameters; a "step" is one pass of the hot path over one batch of `--batch` frames.  Frames are independent, so with
+N GPUs every rank processes its own frame range (no collective; "scaling": "weak") and the value is total frames /
+max-over-ranks device time.  The K timed steps are K consecutive batches of ONE continuous clip: they overlap in the
+slot pipeline the way consecutive seconds of a video do, and the timed region is bracketed by a barrier + full drain
++ synchronize on both sides (pipeline fill and drain are inside it).
 
-  value  frames/s with the inputs already resident in HBM (vsc_submit_device), timed with CUDA
-         events across all slot streams (vsc_timer_begin/end)
-  e2e    frames/s through the public StereoGenerator submit/collect API with pinned HOST buffers:
-         H2D of every frame and D2H of every SBS result are inside the timed region
-  roofline      dominant kernel: algorithmic bytes per frame / its mean device
-                time (CUDA events on its stream), against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
---impl reference times that CPU port alone (the reference itself is Python + OpenCV + torch and
-cannot travel to the GPU box; oracle/ is its restatement).
+  value  frames/s with the inputs already resident in HBM (vsc_submit_device_group), timed with CUDA events across all
+         slot streams (vsc_timer_begin/end)
+  e2e    frames/s through the public StereoGenerator submit / collect API with HOST buffers: every frame's H2D copy
+         (from pinned host memory, where a decoder would leave it) and every SBS frame's D2H copy are inside the timed
+         region; the host sleeps in vsc_wait_any between submissions
+  roofline      dominant kernel: algorithmic bytes per frame / its mean device time (CUDA events on
+                its stream), against MEASURED_PEAKS.json hbm_gbs; `in_load_ms_per_launch` is the same kernel's
+                duration with the pipeline full
+  workloads     the same measurements for BASELINE.json configs[2] / [3]: the 4K (3840x2160, 16-bit depth) clip,
+                frame-sharded over the N GPUs like the headline
+  cpu_baseline  the reference's CPU path timed on this box's host cores, bounded sample (rank 0, N = 1 only)
+--impl reference times the reference's own CPU implementation alone: the UNMODIFIED helper/stereo_core.py staged
+under oracle/_ref by oracle/make_ref.py (cpu_baseline.kind "reference"; every timed step one full 1080p frame), or,
+where that copy is absent, the oracle's C port of it (kind "port").
 """
 from __future__ import annotations
 
@@ -38,15 +42,15 @@ sys.path[:0] = [os.path.join(ROOT, 'video-stereo-converter_b200')]
 
 import numpy as np  # noqa: E402
 
-H, W = 1080, 1920
-DEPTH_DTYPE = np.uint8
-WORKLOAD = '1080p (1920x1080) synthetic clip, uint8 depth, default config.json stereo params'
-N_DISTINCT = 48          # distinct synthetic frames cycled through (inputs 48 * 8.3 MB > 126 MB L2)
-METRIC = 'SBS frames/sec (1080p, default stereo params)'
-if os.environ.get('VSC_BENCH_WORKLOAD') == '4k':    # side measurement (BASELINE.json configs[2]), never the headline line
-    H, W, DEPTH_DTYPE, N_DISTINCT = 2160, 3840, np.uint16, 16
-    WORKLOAD = '4K (3840x2160) synthetic clip, uint16 depth, default config.json stereo params'
-    METRIC = 'SBS frames/sec (4K, 16-bit depth, default stereo params)'
+WORKLOADS = {
+    # distinct frames are cycled; together they exceed the 126 MB L2 (48 x 8.3 MB, 16 x 41 MB of inputs)
+    '1080p': dict(h=1080, w=1920, dtype=np.uint8, distinct=48,
+                  metric='SBS frames/sec (1080p, default stereo params)',
+                  name='1080p (1920x1080) synthetic clip, uint8 depth, default config.json stereo params'),
+    '4k': dict(h=2160, w=3840, dtype=np.uint16, distinct=16,
+               metric='SBS frames/sec (4K, 16-bit depth, default stereo params)',
+               name='4K (3840x2160) synthetic clip, uint16 depth, full-width SBS, default config.json stereo params'),
+}
 
 
 def algorithmic_bytes(h, w, depth_itemsize):
@@ -107,28 +111,30 @@ def make_frames(n, h, w, dtype, seed0=0):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
+def run_workload(key, batch, slots, group, steps, warmup, rank, world, local_rank, dist, profile):
+    """Device-resident leg, end-to-end leg and (rank 0) the per-kernel profile of one workload."""
     import torch
-    from vsc_b200 import StereoGenerator, StereoParams
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from vsc_b200 import StereoGenerator, StereoParams, _lib
+    wl = WORKLOADS[key]
+    H, W, DT = wl['h'], wl['w'], wl['dtype']
     params = StereoParams()
-    slots, batch, group = args.slots, args.batch, args.group
     gen = StereoGenerator(f'cuda:{local_rank}', n_slots=slots, group_size=group)
-    # distinct frames per rank (frame-range shard of the synthetic clip)
-    n_distinct = min(N_DISTINCT, max(batch, slots))
-    frames = make_frames(n_distinct, H, W, DEPTH_DTYPE, seed0=rank * 1000)
+    n_distinct = min(wl['distinct'], max(batch, slots))
+    frames = make_frames(n_distinct, H, W, DT, seed0=rank * 1000)          # this rank's frame range of the synthetic clip
     d_rgb = [torch.from_numpy(r).cuda() for r, _ in frames]
     d_dep = [torch.from_numpy(d).cuda() for _, d in frames]
     d_out = [[torch.empty((H, 2 * W, 3), dtype=torch.uint8, device='cuda') for _ in range(group)] for _ in range(slots)]
+    # the e2e leg's inputs live in pinned host memory, where a decoder / the extractor hand-off would leave them
+    pin_rgb = [_lib.PinnedBuffer((H, W, 3), np.uint8) for _ in range(n_distinct)]
+    pin_dep = [_lib.PinnedBuffer((H, W), DT) for _ in range(n_distinct)]
+    for i, (r, d) in enumerate(frames):
+        np.copyto(pin_rgb[i].array, r)
+        np.copyto(pin_dep[i].array, d)
+    for s_ in range(slots):          # pinned output buffers of every slot, allocated outside the timed region
+        for k_ in range(group):
+            gen.pinned_inputs(s_, H, W, DT, k_)
     torch.cuda.synchronize()
 
-    # The clip is one continuous stream of frames: step k is frames [k*batch, (k+1)*batch) and consecutive steps
-    # overlap in the slot pipeline exactly as consecutive seconds of a video do.  The timed region is bracketed by
-    # a full drain + synchronize on both sides (timed()), never between steps.
     class Pipe:
         def __init__(self):
             self.free, self.busy, self.last = list(range(slots)), [], None
@@ -147,7 +153,7 @@ def run_ours(args, rank, world, local_rank):
             for k in range(min(group, batch - i0)):
                 f = (step * batch + i0 + k) % n_distinct
                 tri.append((d_rgb[f].data_ptr(), d_dep[f].data_ptr(), d_out[s][k].data_ptr()))
-            gen.submit_device_group(s, tri, DEPTH_DTYPE, H, W, params)
+            gen.submit_device_group(s, tri, DT, H, W, params)
             pipe.busy.append(s)
 
     def device_drain(pipe):
@@ -156,13 +162,6 @@ def run_ours(args, rank, world, local_rank):
         pipe.free += pipe.busy
         pipe.busy = []
 
-    from concurrent.futures import ThreadPoolExecutor
-    # loader threads of this rank: never more than its share of the host cores (N ranks share the box)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    loaders = ThreadPoolExecutor(max_workers=max(1, min(group, cores // max(1, world) - 1)))
-    for s_ in range(slots):          # allocate the pinned staging buffers outside the timed region
-        for k_ in range(group):
-            gen.pinned_inputs(s_, H, W, DEPTH_DTYPE, k_)
     e2e_reads = []
 
     def e2e_step(step, pipe):
@@ -173,16 +172,8 @@ def run_ours(args, rank, world, local_rank):
                 pipe.busy.remove(s)
                 pipe.free.append(s)
             s = pipe.free.pop(0)
-            n = min(group, batch - i0)
-
-            def load(k, s=s, i0=i0):
-                # the loader pool's job: decode straight into the slot's pinned buffers (here: memcpy of a prepared frame)
-                f = (step * batch + i0 + k) % n_distinct
-                prgb, pdep = gen.pinned_inputs(s, H, W, DEPTH_DTYPE, k)
-                np.copyto(prgb, frames[f][0])
-                np.copyto(pdep, frames[f][1])
-            list(loaders.map(load, range(n)))
-            gen.submit_pinned(s, params, n)
+            idx = [(step * batch + i0 + k) % n_distinct for k in range(min(group, batch - i0))]
+            gen.submit_host(s, [(pin_rgb[f].array, pin_dep[f].array) for f in idx], params)
             pipe.busy.append(s)
         if pipe.last is not None:        # host read of the newest finished SBS frame (pinned, already transferred)
             last = pipe.last[-1] if isinstance(pipe.last, list) else pipe.last
@@ -201,12 +192,12 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, drain, steps):
+    def timed(fn, drain, nsteps):
         pipe = Pipe()
         barrier()
         gen.timer_begin()
         t0 = time.perf_counter()
-        for k in range(steps):
+        for k in range(nsteps):
             fn(k, pipe)
         drain(pipe)
         ms = gen.timer_end()
@@ -219,83 +210,121 @@ def run_ours(args, rank, world, local_rank):
         return ms, wall
 
     wp = Pipe()
-    for k in range(args.warmup):
+    for k in range(warmup):
         device_step(k, wp)
     device_drain(wp)
     launches_per_frame = gen.last_frame_launches(0) / group
     with ClockSampler(local_rank) as clk:
-        ms_dev, wall_dev = timed(device_step, device_drain, args.steps)
+        ms_dev, wall_dev = timed(device_step, device_drain, steps)
     wp = Pipe()
-    for k in range(max(1, args.warmup // 2)):
+    for k in range(max(1, warmup // 2)):
         e2e_step(k, wp)
     e2e_drain(wp)
-    ms_e2e, wall_e2e = timed(e2e_step, e2e_drain, args.steps)
+    ms_e2e, wall_e2e = timed(e2e_step, e2e_drain, steps)
 
-    # per-kernel times for the roofline (separate, untimed pass with event pairs around every launch)
-    kt = {}          # kernel name -> list over profiled frames of its summed device ms in that frame
-    if rank == 0:
+    # per-kernel times for the roofline (separate, untimed passes with event pairs around every launch): first one slot
+    # submission in flight at a time ("solo"), then with every slot busy ("in load", the regime `value` is measured in)
+    kt, kt_load = {}, {}
+    if rank == 0 and profile:
         gen.set_profiling(True)
-        # one slot submission (`group` frames sharing one hole-filling launch sequence) in flight at a time, exactly
-        # the launch structure of the timed legs; times are divided by the frames per submission
-        nprof = 6
-        for i in range(nprof):
-            tri = [(d_rgb[(i * group + k) % n_distinct].data_ptr(), d_dep[(i * group + k) % n_distinct].data_ptr(),
-                    d_out[0][k].data_ptr()) for k in range(group)]
-            gen.submit_device_group(0, tri, DEPTH_DTYPE, H, W, params)
+
+        def tri_for(i, s):
+            return [(d_rgb[(i * group + k) % n_distinct].data_ptr(), d_dep[(i * group + k) % n_distinct].data_ptr(),
+                     d_out[s][k].data_ptr()) for k in range(group)]
+
+        def harvest(dst, s):
+            per = {}
+            for name, t in gen.kernel_times(s):
+                per[name] = per.get(name, 0.0) + t / group
+            for name, t in per.items():
+                dst.setdefault(name, []).append(t)
+        for i in range(6):
+            gen.submit_device_group(0, tri_for(i, 0), DT, H, W, params)
             gen.wait(0)
             if i >= 2:
-                per = {}
-                for name, t in gen.kernel_times(0):
-                    per[name] = per.get(name, 0.0) + t / group
-                for name, t in per.items():
-                    kt.setdefault(name, []).append(t)
+                harvest(kt, 0)
+        for rnd in range(3):
+            for s in range(slots):
+                gen.submit_device_group(s, tri_for(rnd * slots + s, s), DT, H, W, params)
+            for s in range(slots):
+                gen.wait(s)
+                if rnd >= 1:
+                    harvest(kt_load, s)
         gen.set_profiling(False)
-    frames_total = batch * args.steps * world
-    out = None
+    frames_total = batch * steps * world
+    bytes_frame = algorithmic_bytes(H, W, np.dtype(DT).itemsize)
+    in_bytes = H * W * 3 + H * W * np.dtype(DT).itemsize
+    out_bytes = H * 2 * W * 3
+    res = None
     if rank == 0:
         peak, peak_src = hbm_peak()
-        per_kernel = {k: float(np.mean(v)) for k, v in kt.items()}   # device ms per frame, one slot submission in flight
-        # launches of a kernel per slot submission: the hole-filling kernels run once for all `group` frames
-        per_launch = {k: per_kernel[k] * (group if k.startswith('telea_') else 1) for k in per_kernel}
-        frame_serial = float(sum(per_kernel.values()))
-        dom = max(per_kernel, key=per_kernel.get)
-        bytes_frame = algorithmic_bytes(H, W, np.dtype(DEPTH_DTYPE).itemsize)
-        achieved = bytes_frame / (per_kernel[dom] * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')) as f:
-                tj = json.load(f)
-                if tj.get('kernel') == dom:
-                    traffic = tj.get('dram_bytes_per_launch')
-        except Exception:
-            pass
-        out = {
-            'metric': METRIC, 'value': frames_total / (ms_dev * 1e-3), 'unit': 'frames/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'frames_per_step_per_gpu': batch, 'slots_in_flight': slots, 'frames_per_slot': group,
+        fps, fps_e2e = frames_total / (ms_dev * 1e-3), frames_total / (ms_e2e * 1e-3)
+        res = {
+            'metric': wl['metric'], 'value': fps, 'unit': 'frames/s', 'ms_per_step': ms_dev / steps,
+            'config': {'workload': wl['name'], 'frames_per_step_per_gpu': batch, 'slots_in_flight': slots, 'frames_per_slot': group,
                        'distinct_frames': n_distinct, 'l2_policy': 'inputs larger than L2 (%d distinct frames cycled)' % n_distinct,
                        'sharding': 'frame-range, no collective'},
-            'e2e': {'value': frames_total / (ms_e2e * 1e-3), 'unit': 'frames/s',
-                    'h2d_bytes_per_step': batch * (H * W * 3 + H * W * np.dtype(DEPTH_DTYPE).itemsize),
-                    'd2h_bytes_per_step': batch * H * 2 * W * 3, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(round(launches_per_frame * batch * args.steps)),
-            'launches_per_frame': launches_per_frame,
-            'clocks': clk.summary(),
-            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': bytes_frame * (group if dom.startswith('telea_') else 1),
-                         'frames_per_launch': group if dom.startswith('telea_') else 1,
-                         'kernel_ms_per_launch': per_launch[dom], 'kernel_ms_per_frame': per_kernel[dom],
-                         'share_of_serial_frame': per_kernel[dom] / frame_serial if frame_serial else None,
-                         'whole_path': {'achieved': frames_total / world / (ms_dev * 1e-3) * bytes_frame / 1e9,
-                                        'frac': frames_total / world / (ms_dev * 1e-3) * bytes_frame / 1e9 / peak}},
-            'kernel_ms_per_frame': {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
-            'wall_ms': {'device_leg': wall_dev, 'e2e_leg': wall_e2e},
+            'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': batch * in_bytes, 'd2h_bytes_per_step': batch * out_bytes,
+                    'ms_per_step': ms_e2e / steps, 'h2d_gbs_per_rank': fps_e2e / world * in_bytes / 1e9,
+                    'd2h_gbs_per_rank': fps_e2e / world * out_bytes / 1e9,
+                    'host_side': 'inputs pre-staged in pinned host memory, no per-frame host copy; the submitting thread sleeps in vsc_wait_any'},
+            'gpu_launches': int(round(launches_per_frame * batch * steps)), 'launches_per_frame': launches_per_frame,
+            'clocks': clk.summary(), 'wall_ms': {'device_leg': wall_dev, 'e2e_leg': wall_e2e},
+            'whole_path': {'achieved': fps / world * bytes_frame / 1e9, 'frac': fps / world * bytes_frame / 1e9 / peak, 'unit': 'GB/s'},
         }
+        if kt:
+            per_kernel = {k: float(np.mean(v)) for k, v in kt.items()}   # device ms per frame, one slot submission in flight
+            per_load = {k: float(np.mean(v)) for k, v in kt_load.items()}
+            grp = lambda k: group if k.startswith('telea_') else 1       # hole-filling kernels: one launch per slot submission
+            frame_serial = float(sum(per_kernel.values()))
+            dom = max(per_kernel, key=per_kernel.get)
+            achieved = bytes_frame / (per_kernel[dom] * 1e-3) / 1e9
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')) as f:
+                    tj = json.load(f)
+                    if tj.get('kernel') == dom and tj.get('workload', '1080p') == key:
+                        traffic = tj.get('dram_bytes_per_launch')
+            except Exception:
+                pass
+            res['roofline'] = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                               'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                               'algorithmic_bytes_per_launch': bytes_frame * grp(dom), 'frames_per_launch': grp(dom),
+                               'kernel_ms_per_launch': per_kernel[dom] * grp(dom), 'kernel_ms_per_frame': per_kernel[dom],
+                               'in_load_ms_per_launch': per_load.get(dom, 0.0) * grp(dom) or None,
+                               'share_of_serial_frame': per_kernel[dom] / frame_serial if frame_serial else None,
+                               'whole_path': res['whole_path']}
+            res['kernel_ms_per_frame'] = {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+            res['kernel_ms_per_frame_in_load'] = {k: round(v, 4) for k, v in sorted(per_load.items(), key=lambda kv: -kv[1])}
+    gen.close()
+    for b in pin_rgb + pin_dep:
+        b.free()
+    del d_rgb, d_dep, d_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    head = run_workload('1080p', args.batch, args.slots, args.group, args.steps, args.warmup, rank, world, local_rank, dist, True)
+    extra = None
+    if not args.no_4k:
+        extra = run_workload('4k', args.batch_4k, args.slots_4k, args.group, args.steps, args.warmup, rank, world, local_rank, dist, True)
+    out = None
+    if rank == 0:
+        out = {'metric': head['metric'], 'value': head['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+               'warmup': args.warmup, 'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+               'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic'}
+        out.update({k: v for k, v in head.items() if k not in ('metric', 'value', 'unit', 'ms_per_step', 'whole_path')})
+        if extra is not None:
+            out['workloads'] = {'4k': extra}
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(sample_frames=args.cpu_frames)
-    gen.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -306,53 +335,101 @@ def _use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     os.environ['OMP_NUM_THREADS'] = str(n)
+    return n
 
 
-def cpu_baseline(sample_frames=1, h=H, w=W, warm=False):
-    """Oracle port of the reference CPU path on this box's host cores (bounded sample)."""
+def _reference_generator():
+    """The unmodified reference module (oracle/_ref or /root/reference), or None."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    try:
+        import ref_runner
+        if not ref_runner.reference_available():
+            return None, ''
+        n = _use_all_host_threads()
+        import cv2
+        import torch
+        torch.set_num_threads(n)
+        cv2.setNumThreads(n)
+        sc = ref_runner.import_reference()
+        return sc, ref_runner.reference_origin()
+    except Exception as e:       # pragma: no cover - reported in the JSON line
+        return None, f'unavailable: {e}'
+
+
+def cpu_baseline(sample_frames=1):
+    """The reference's CPU path on this box's host cores, bounded sample of the headline workload: the unmodified
+    reference when it is staged here (one 1080p frame after a warm-up band), else the oracle's C port."""
+    wl = WORKLOADS['1080p']
+    H, W = wl['h'], wl['w']
+    sc, origin = _reference_generator()
+    if sc is not None:
+        import torch
+        frames = make_frames(2, H, W, wl['dtype'], seed0=0)
+        g = sc.StereoGenerator('cpu')
+        g.process_frame(frames[0][0][:136], frames[0][1][:136], sc.StereoParams())      # warm-up band
+        t0 = time.perf_counter()
+        n = max(1, min(2, sample_frames))
+        for r, d in frames[:n]:
+            g.process_frame(r, d, sc.StereoParams())
+        dt = time.perf_counter() - t0
+        return {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'reference',
+                'sample': f'{n} synthetic {W}x{H} frame(s), default params, unmodified helper/stereo_core.py '
+                          f'StereoGenerator("cpu").process_frame ({origin}), torch {torch.get_num_threads()} threads; {dt:.1f} s',
+                'host_cpus': os.cpu_count()}
     _use_all_host_threads()
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle as O
     O.build()
-    frames = make_frames(sample_frames, h, w, DEPTH_DTYPE, seed0=0)
-    if warm:
-        O.process_frame(frames[0][0][:64], frames[0][1][:64], O.Params())
+    frames = make_frames(sample_frames, H, W, wl['dtype'], seed0=0)
     t0 = time.perf_counter()
     for r, d in frames:
         O.process_frame(r, d, O.Params())
     dt = time.perf_counter() - t0
-    return {'value': sample_frames * (h / H) / dt, 'unit': 'frames/s', 'cores': O.num_threads(), 'kind': 'port',
-            'sample': f'{sample_frames} synthetic {w}x{h} frame(s), default params, oracle/ C+numpy port of '
-                      f'helper/stereo_core.py with OpenMP ({O.num_threads()} threads); {dt:.1f} s',
+    return {'value': sample_frames / dt, 'unit': 'frames/s', 'cores': O.num_threads(), 'kind': 'port',
+            'sample': f'{sample_frames} synthetic {W}x{H} frame(s), default params, oracle/ C+numpy port of '
+                      f'helper/stereo_core.py with OpenMP ({O.num_threads()} threads); {dt:.1f} s (reference not staged: {origin or "oracle/_ref absent"})',
             'host_cpus': os.cpu_count()}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the reference's own implementation, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation on the host cores, rank 0 only."""
     if rank != 0:
         return None
-    _use_all_host_threads()
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import oracle as O
-    O.build()
-    total = args.steps + args.warmup
-    rows = H if total <= 16 else max(136, (H * 16 // total) // 8 * 8)
-    if os.environ.get('VSC_BENCH_TINY'):     # unit tests only: keep the CPU suite fast
-        rows = 64
-    frames = make_frames(2, rows, W, DEPTH_DTYPE, seed0=0)
+    wl = WORKLOADS['1080p']
+    H, W = wl['h'], wl['w']
+    tiny = bool(os.environ.get('VSC_BENCH_TINY'))     # unit tests only: keep the CPU suite fast
+    rows = 64 if tiny else H
+    frames = make_frames(2, rows, W, wl['dtype'], seed0=0)
+    sc, origin = (None, 'VSC_BENCH_FORCE_PORT') if os.environ.get('VSC_BENCH_FORCE_PORT') else _reference_generator()
+    if sc is not None:
+        import torch
+        g, p = sc.StereoGenerator('cpu'), sc.StereoParams()
+        step = lambda k: g.process_frame(frames[k % 2][0], frames[k % 2][1], p)
+        warm = lambda k: g.process_frame(frames[k % 2][0][:min(rows, 272)], frames[k % 2][1][:min(rows, 272)], p)
+        kind, cores = 'reference', torch.get_num_threads()
+        what = f'unmodified helper/stereo_core.py StereoGenerator("cpu").process_frame ({origin})'
+    else:
+        _use_all_host_threads()
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import oracle as O
+        O.build()
+        step = lambda k: O.process_frame(frames[k % 2][0], frames[k % 2][1], O.Params())
+        warm = lambda k: O.process_frame(frames[k % 2][0][:min(rows, 272)], frames[k % 2][1][:min(rows, 272)], O.Params())
+        kind, cores = 'port', O.num_threads()
+        what = f'oracle/ C+numpy port of helper/stereo_core.py (reference not staged: {origin or "oracle/_ref absent"})'
     for k in range(args.warmup):
-        O.process_frame(*frames[k % 2], O.Params())
+        warm(k)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        O.process_frame(*frames[k % 2], O.Params())
+        step(k)
     dt = time.perf_counter() - t0
     value = args.steps * (rows / H) / dt
-    base = {'value': value, 'unit': 'frames/s', 'cores': O.num_threads(), 'kind': 'port',
-            'sample': f'each step = one synthetic {W}x{rows} frame ({rows}/{H} of a 1080p frame), default params'}
-    return {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s',
+    base = {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+            'sample': f'each timed step = one full synthetic {W}x{rows} frame, default params, {what}; warm-up steps use a {min(rows, 272)}-row band'}
+    return {'impl': 'reference', 'metric': wl['metric'], 'value': value, 'unit': 'frames/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'note': 'CPU port (oracle/) of helper/stereo_core.py; the Python reference cannot travel to the GPU box'},
+            'config': {'workload': wl['name'], 'note': what},
             'cpu_baseline': base, 'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
 
@@ -363,10 +440,13 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=300, help='frames per step per GPU (BASELINE.json configs[1]: a 300-frame clip)')
-    ap.add_argument('--slots', type=int, default=30, help='slots (CUDA streams) per GPU')
+    ap.add_argument('--batch', type=int, default=300, help='1080p frames per step per GPU (BASELINE.json configs[1]: a 300-frame clip)')
+    ap.add_argument('--slots', type=int, default=16, help='slots (CUDA streams) per GPU, 1080p')
     ap.add_argument('--group', type=int, default=4, help='frames per slot submission (share a stream and one hole-filling launch)')
-    ap.add_argument('--cpu-frames', type=int, default=4, help='frames of the bounded CPU-baseline sample (about 3 s each on 16 threads)')
+    ap.add_argument('--batch-4k', type=int, default=64, help='4K frames per step per GPU')
+    ap.add_argument('--slots-4k', type=int, default=10, help='slots per GPU at 4K (2.75 GB per frame in flight)')
+    ap.add_argument('--no-4k', action='store_true', help='skip the 4K workload')
+    ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -107,6 +107,10 @@ int vsc_submit_device_group(vsc_ctx *ctx, int slot, int n, const uint8_t *const 
 int vsc_wait(vsc_ctx *ctx, int slot);
 /* non-blocking: 1 if the slot's frame has finished (vsc_wait will not block), 0 if it is still running */
 int vsc_query(vsc_ctx *ctx, int slot);
+/* Sleep (no polling) until one of the n in-flight slots has finished on the device, or timeout_ms has passed
+ * (< 0: no timeout).  *which = that slot (still to be vsc_wait'ed, which then returns at once) or -1 on timeout.
+ * The frame loop's replacement for the reference's blocking queue get (sbs_generator.py:243-246). */
+int vsc_wait_any(vsc_ctx *ctx, const int *slots, int n, int timeout_ms, int *which);
 /* device-resident variant: inputs/outputs are device pointers on ctx's device; enqueues only
  * (no copies, no synchronisation); vsc_wait(slot) or vsc_sync to complete. */
 int vsc_submit_device(vsc_ctx *ctx, int slot, const uint8_t *d_rgb, const void *d_depth, int depth_dtype,

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [fixture names]
 
 Each fixture holds the synthetic inputs, the stereo parameters, the reference's SBS output, its hole
 masks (bit-packed) and SHA-256 digests of the larger intermediates, produced by importing
@@ -47,6 +47,16 @@ CASES = {
 }
 
 
+# Full-size frames: the reference's SBS output is not stored (12 MB of noise per 1080p frame).  The fixture holds its
+# SHA-256 plus the sparse list of values in which it differs from the ORACLE's output at generation time, so a test
+# can rebuild the reference's frame exactly (oracle output + patches), prove it with the digest, and then apply the
+# tolerance to the oracle and to the CUDA path.  Inputs are regenerated from the seed.
+BIG_CASES = {
+    'full_1080p_u8': ((1080, 1920), np.uint8, 0, {}),
+    'band_4k_u16': ((256, 3840), np.uint16, 1, {}),
+}
+
+
 def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -54,9 +64,12 @@ def sha(a: np.ndarray) -> str:
 def main():
     import cv2
     import torch
-    out_dir = os.path.join(ROOT, 'tests', 'golden')
+    out_dir = os.environ.get('VSC_GOLDEN_OUT', os.path.join(ROOT, 'tests', 'golden'))
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])          # optional: fixture names to (re)generate
     for name, (shape, dt, seed, kw) in CASES.items():
+        if only and name not in only:
+            continue
         if dt == 'flat':
             rgb, _ = make_pair(*shape, seed=seed)
             depth = np.full(shape, 77, np.uint8)
@@ -65,9 +78,13 @@ def main():
             rgb = np.ones(shape + (3,), np.uint8)
         else:
             rgb, depth = make_pair(*shape, seed=seed, depth_dtype=dt)
+        cv2.ipp.setUseIPP(True)
         r = ref_runner.run_reference(rgb, depth, kw)
+        cv2.ipp.setUseIPP(False)       # OpenCV's own (documented) code paths instead of the closed-source IPP ones
+        sbs_noipp = ref_runner.run_reference(rgb, depth, kw, taps=False)['sbs']
+        cv2.ipp.setUseIPP(True)
         fx = dict(rgb=rgb, depth=depth, params=np.array(json.dumps(kw)),
-                  sbs=r['sbs'],
+                  sbs=r['sbs'], sbs_noipp=sbs_noipp,
                   mask_left=np.packbits(r['mask_left']), mask_right=np.packbits(r['mask_right']), mask_shape=np.array(r['mask_left'].shape),
                   sha_rgb_stretched=sha(r['rgb_stretched']), sha_depth_stretched=sha(r['depth_stretched']),
                   sha_depth_norm=sha(r['depth_norm']), sha_rgb_ss=sha(r['rgb_ss']),
@@ -77,7 +94,29 @@ def main():
         if 'depth_soft' in r:
             fx['sha_depth_soft'] = sha(r['depth_soft'])
         np.savez_compressed(os.path.join(out_dir, name + '.npz'), **fx)
-        print(name, shape, r['sbs'].shape, 'holes L/R', int((r['mask_left'] == 0).sum()), int((r['mask_right'] == 0).sum()))
+        print(name, shape, r['sbs'].shape, 'holes L/R', int((r['mask_left'] == 0).sum()), int((r['mask_right'] == 0).sum()),
+              'IPP on/off differ in', int((r['sbs'] != sbs_noipp).sum()), 'values')
+    import oracle as O
+    for name, (shape, dt, seed, kw) in BIG_CASES.items():
+        if only and name not in only:
+            continue
+        rgb, depth = make_pair(*shape, seed=seed, depth_dtype=dt)
+        cv2.ipp.setUseIPP(True)
+        r = ref_runner.run_reference(rgb, depth, kw)
+        cv2.ipp.setUseIPP(False)
+        sbs_noipp = ref_runner.run_reference(rgb, depth, kw, taps=False)['sbs']
+        cv2.ipp.setUseIPP(True)
+        mine = O.process_frame(rgb, depth, O.Params(**kw))
+        fx = dict(shape=np.array(shape), seed=np.array(seed), depth_dtype=np.array(np.dtype(dt).name), params=np.array(json.dumps(kw)),
+                  sha_sbs=sha(r['sbs']), sha_sbs_noipp=sha(sbs_noipp),
+                  sha_mask_left=sha(np.packbits(r['mask_left'])), sha_mask_right=sha(np.packbits(r['mask_right'])),
+                  versions=np.array([torch.__version__, cv2.__version__, np.__version__]))
+        for tag, ref in (('', r['sbs']), ('_noipp', sbs_noipp)):
+            idx = np.flatnonzero(ref.ravel() != mine.ravel())
+            fx['patch_idx' + tag] = idx.astype(np.int64)
+            fx['patch_val' + tag] = ref.ravel()[idx]
+        np.savez_compressed(os.path.join(out_dir, name + '.big.npz'), **fx)
+        print(name, shape, 'oracle differs from the reference in', len(fx['patch_idx']), 'values (IPP) /', len(fx['patch_idx_noipp']), '(IPP off)')
 
 
 if __name__ == '__main__':

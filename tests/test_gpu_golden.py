@@ -10,7 +10,8 @@ import pytest
 
 import oracle as O
 from conftest import ROOT
-from test_oracle_golden import GOLDEN, check_sbs_against_reference, load
+from test_oracle_golden import (GOLDEN, GOLDEN_BIG, big_inputs, check_sbs_against_reference, fixture_name, load,
+                                rebuild_reference, sha)
 from vsc_b200 import StereoGenerator, StereoParams, _lib
 from vsc_b200.synthetic import make_pair
 
@@ -25,11 +26,24 @@ def gen():
     g.close()
 
 
-@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize('path', GOLDEN_BIG, ids=[fixture_name(p) for p in GOLDEN_BIG])
+def test_cuda_matches_reference_full_size(gen, path):
+    """Full 1080p frame / 3840-wide band against the reference's own output (rebuilt from the fixture's patches and
+    proven by its digest): the pinned distance, with and without IPP."""
+    z, kw = load(path)
+    rgb, depth = big_inputs(z)
+    out = gen.process_frame(rgb, depth, StereoParams(**kw))
+    name = fixture_name(path)
+    check_sbs_against_reference(out, rebuild_reference(z, out), name, 'ipp')
+    check_sbs_against_reference(out, rebuild_reference(z, out, '_noipp'), name, 'noipp')
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[fixture_name(p) for p in GOLDEN])
 def test_cuda_matches_reference_golden(gen, path):
     z, kw = load(path)
     out = gen.process_frame(z['rgb'], z['depth'], StereoParams(**kw))
-    check_sbs_against_reference(out, z['sbs'], kw)
+    check_sbs_against_reference(out, z['sbs'], fixture_name(path), 'ipp')
+    check_sbs_against_reference(out, z['sbs_noipp'], fixture_name(path), 'noipp')
     # hole masks / shift indices as the reference produced them: bit-exact (stage-wise, through the C ABI)
     lib = _lib.load()
     h, w = z['rgb'].shape[:2]

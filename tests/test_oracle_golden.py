@@ -3,9 +3,9 @@ generator oracle/make_golden.py, reference = /root/reference/helper/stereo_core.
 
 Pins, per SURVEY.md 8(c): integer stages (Lanczos stretch, warp indices / hole masks) bit-exact;
 the float depth front end bit-exact up to apply_depth_gamma, whose torch.pow (Sleef, <= 1 ulp) is
-the only float op the oracle does not reproduce bit for bit; final SBS within 1 LSB with a bounded
-mismatch fraction (bilateral: cv2's IPP build differs from the documented algorithm on ~1e-5 of the
-values).  The same fixtures are compared with the CUDA path in test_gpu_golden.py.
+the only float op the oracle does not reproduce bit for bit; final SBS at a pinned per-fixture distance
+from the reference, both as shipped (cv2's IPP bilateral) and with IPP switched off (BOUNDS below).
+The same fixtures are compared with the CUDA path in test_gpu_golden.py.
 """
 import glob
 import hashlib
@@ -17,25 +17,48 @@ import pytest
 
 import oracle as O
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz')))
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if not p.endswith('.big.npz'))
+GOLDEN_BIG = sorted(glob.glob(os.path.join(HERE, 'golden', '*.big.npz')))
+
+# Measured distance of this repository's result (oracle == CUDA path, bit for bit) from the UNMODIFIED reference, per
+# fixture: (values that differ, values that differ by more than 1 LSB, largest difference), against the reference as
+# shipped (cv2 with its closed-source IPP bilateral) and against the reference run with cv2.ipp.setUseIPP(False)
+# (OpenCV's own documented code).  These are pins, not budgets: a change that moves any of them fails.
+#   * everything upstream of the bilateral filter is bit-exact (digests below), so are the hole masks;
+#   * with IPP off the residual is <= 3 values per small frame: the 5x5 unsharp blur's float summation order (+-1 ulp,
+#     amplified 15x before the truncation) and, in aggressive_band_in_crop, two 1-LSB differences of the 149-tap
+#     bilateral (2 of 1.4 M values) that the unsharp mask amplifies to 3 LSB in three output values;
+#   * the shipped IPP bilateral differs from OpenCV's own on ~1e-5 of the super-sampled values, each such
+#     value can be amplified up to 15x by the unsharp mask: 2 of 12 fixtures exceed 1 LSB against the IPP build.
+BOUNDS = {
+    'aggressive_band_in_crop': {'ipp': (8, 3, 3), 'noipp': (3, 1, 3)},
+    'default_u16': {'ipp': (35, 0, 1), 'noipp': (2, 0, 1)},
+    'default_u8': {'ipp': (15, 0, 1), 'noipp': (2, 0, 1)},
+    'flat_depth': {'ipp': (9, 0, 1), 'noipp': (3, 0, 1)},
+    'float_depth': {'ipp': (9, 4, 6), 'noipp': (0, 0, 0)},
+    'min_sliders': {'ipp': (1, 0, 1), 'noipp': (0, 0, 0)},
+    'near_black': {'ipp': (0, 0, 0), 'noipp': (0, 0, 0)},
+    'ss1_sharp_edges': {'ipp': (0, 0, 0), 'noipp': (0, 0, 0)},
+    'ss2p5_nosmooth_nosharpen': {'ipp': (0, 0, 0), 'noipp': (0, 0, 0)},
+    'ss4_max_sliders': {'ipp': (0, 0, 0), 'noipp': (0, 0, 0)},
+    'full_1080p_u8': {'ipp': (1410, 3, 2), 'noipp': (70, 1, 2)},         # 1.1e-4 / 5.6e-6 of 12.4 M values
+    'band_4k_u16': {'ipp': (733, 0, 1), 'noipp': (34, 0, 1)},           # 1.2e-4 / 5.8e-6 of 5.9 M values
+}
 
 
-def check_sbs_against_reference(out, ref, kw):
-    """Tolerance of a final SBS frame against the reference's own output.
+def fixture_name(path):
+    return os.path.basename(path).split('.')[0]
 
-    Without artifact smoothing the path is integer-exact up to torch.pow's last ulp: <= 1 LSB.
-    With smoothing, cv2's default (closed-source IPP) bilateral differs from OpenCV's documented
-    algorithm by 1 LSB on ~1e-5 of the super-sampled values; such a value can then be read
-    by the inpainting and is amplified up to 15x by the unsharp mask, so a handful of output values may
-    be off by a few LSB.  Measured on these fixtures: <= 35 differing values per frame (<= 3e-4), at most
-    4 of them above 1 LSB (max 6); against the reference run with cv2.ipp.setUseIPP(False): <= 3 values.
-    """
+
+def check_sbs_against_reference(out, ref, name, which='ipp'):
+    """Distance of a final SBS frame from the reference's own output: the per-fixture pins above."""
+    assert out.shape == ref.shape
     diff = np.abs(out.astype(int) - ref.astype(int))
-    assert (diff > 0).mean() < 5e-4, f'{(diff > 0).sum()} of {diff.size} values differ'
-    if kw.get('artifact_smoothing', 1.0) == 0:
-        assert diff.max() <= 1, f'max abs error {diff.max()}'
-    else:
-        assert (diff > 1).sum() <= 8 and diff.max() <= 8, f'{(diff > 1).sum()} values above 1 LSB, max {diff.max()}'
+    n, n1, mx = BOUNDS[name][which]
+    got = (int((diff > 0).sum()), int((diff > 1).sum()), int(diff.max()))
+    assert got[0] <= n and got[1] <= n1 and got[2] <= mx, f'{name} vs reference ({which}): {got} exceeds the pinned {(n, n1, mx)}'
+    assert (diff > 0).mean() < 5e-4
 
 
 def sha(a):
@@ -48,7 +71,7 @@ def load(path):
     return z, kw
 
 
-@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize('path', GOLDEN, ids=[fixture_name(p) for p in GOLDEN])
 def test_oracle_matches_reference_golden(path):
     z, kw = load(path)
     taps = {}
@@ -73,9 +96,58 @@ def test_oracle_matches_reference_golden(path):
         assert np.array_equal(taps['mask_' + side], ref_mask), side
         assert sha(taps['warp_' + side]) == str(z['sha_warp_' + side]), side
     # final frame: +-1 LSB, tiny mismatch fraction
-    ref = z['sbs']
-    assert out.shape == ref.shape
-    check_sbs_against_reference(out, ref, kw)
+    name = fixture_name(path)
+    check_sbs_against_reference(out, z['sbs'], name, 'ipp')
+    check_sbs_against_reference(out, z['sbs_noipp'], name, 'noipp')
+
+
+def rebuild_reference(z, mine, tag=''):
+    """The reference's full-size SBS frame = this repository's frame + the fixture's sparse patches, proven by the
+    fixture's SHA-256 of the reference output."""
+    ref = mine.copy().ravel()
+    ref[z['patch_idx' + tag]] = z['patch_val' + tag]
+    assert sha(ref) == str(z['sha_sbs' + tag]), 'rebuilt frame is not the reference frame: the result moved'
+    return ref.reshape(mine.shape)
+
+
+def big_inputs(z):
+    from vsc_b200.synthetic import make_pair
+    h, w = (int(v) for v in z['shape'])
+    return make_pair(h, w, seed=int(z['seed']), depth_dtype=np.dtype(str(z['depth_dtype'])))
+
+
+@pytest.mark.parametrize('path', GOLDEN_BIG, ids=[fixture_name(p) for p in GOLDEN_BIG])
+def test_oracle_matches_reference_full_size(path):
+    """Full 1080p frame and a 3840-wide band (the 4K geometry, stretched_w 3949): hole masks bit-exact, SBS at the
+    pinned distance from the reference with and without IPP."""
+    z, kw = load(path)
+    rgb, depth = big_inputs(z)
+    taps = {}
+    out = O.process_frame(rgb, depth, O.Params(**kw), taps)
+    for side in ('left', 'right'):
+        assert sha(np.packbits(taps['mask_' + side])) == str(z['sha_mask_' + side]), side
+    name = fixture_name(path)
+    check_sbs_against_reference(out, rebuild_reference(z, out), name, 'ipp')
+    check_sbs_against_reference(out, rebuild_reference(z, out, '_noipp'), name, 'noipp')
+
+
+def test_golden_recipe_reproduces_a_committed_fixture(tmp_path):
+    """oracle/make_golden.py, run as committed, regenerates a fixture identical to the committed file (needs the
+    reference tree or its staged copy; the recipe loads the reference module by file path)."""
+    import subprocess
+    import sys
+    import ref_runner
+    if not ref_runner.reference_available():
+        pytest.skip('reference tree not available here')
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, VSC_GOLDEN_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(root, 'oracle', 'make_golden.py'), 'min_sliders'], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    new, old = np.load(tmp_path / 'min_sliders.npz'), np.load(os.path.join(HERE, 'golden', 'min_sliders.npz'))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        if k != 'versions':
+            assert np.array_equal(new[k], old[k]), k
 
 
 def test_oracle_is_deterministic():

@@ -14,6 +14,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -259,6 +262,9 @@ struct Slot {
     int l_dtype = 0, l_H = 0, l_W = 0; vsc_params l_p; uint8_t* l_host_out = nullptr; size_t l_out_bytes = 0;
     int launches = 0;
     float last_ms = 0.f;
+    bool done = false;                   // leader only: the stream has run past the submission (set by a host callback)
+    struct vsc_ctx* owner = nullptr;
+    bool prof = false;                   // per-kernel event pairs (vsc_set_profiling)
     // optional per-kernel profiling (vsc_set_profiling): event pairs around every launch
     std::vector<cudaEvent_t> pev;
     std::vector<const char*> pname;
@@ -274,6 +280,8 @@ struct vsc_ctx {
     std::vector<cudaEvent_t> tslot;
     int sm_count = 148;
     std::vector<Slot> slots;
+    std::mutex mu;                       // guards Slot::done; vsc_wait_any sleeps on cv until a submission completes
+    std::condition_variable cv;
     DevBuf color_w;     // bilateral colour LUT for sigmaColor = 30 (stereo_core.py:410)
     DevBuf pow_tab;     // tables of the deterministic pow (apply_depth_gamma)
 };
@@ -377,6 +385,7 @@ extern "C" int vsc_create_grouped(int device, int n_groups, int group_size, vsc_
     ctx->slots.resize((size_t)n_groups * group_size);
     for (size_t i = 0; i < ctx->slots.size(); i++) {
         Slot& s = ctx->slots[i];
+        s.owner = ctx;
         bool ok = true;
         if (i % group_size == 0) {
             ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -408,11 +417,17 @@ extern "C" void vsc_destroy(vsc_ctx* ctx) {
                           &s.tile_u8[0], &s.tile_u8[1], &s.tile_i32[0], &s.tile_i32[1], &s.qkey[0], &s.qkey[1],
                           &s.qidx[0], &s.qidx[1], &s.tabs, &s.scalars};
         for (DevBuf* b : bufs) b->release();
+        s.tstats.release();
+        for (cudaEvent_t e : s.pev) cudaEventDestroy(e);
         if (s.h_scalars) cudaFreeHost(s.h_scalars);
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
         if (s.stream && s.owns_stream) cudaStreamDestroy(s.stream);
     }
+    for (cudaEvent_t e : ctx->tslot) cudaEventDestroy(e);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->tstream) cudaStreamDestroy(ctx->tstream);
     ctx->color_w.release();
     ctx->pow_tab.release();
     delete ctx;
@@ -463,16 +478,15 @@ static int ensure_tables(Slot& s, const vsc_geom& g) {
     return VSC_OK;
 }
 
-static bool g_profiling = false;   // mirrors ctx->profiling for the launch helpers
 static void prof_begin(Slot& s, const char* name) {
-    if (!g_profiling) return;
+    if (!s.prof) return;
     while ((int)s.pev.size() < 2 * (s.pcount + 1)) { cudaEvent_t e; cudaEventCreate(&e); s.pev.push_back(e); }
     if ((int)s.pname.size() <= s.pcount) s.pname.resize(s.pcount + 1);
     s.pname[s.pcount] = name;
     cudaEventRecord(s.pev[2 * s.pcount], s.stream);
 }
 static void prof_end(Slot& s) {
-    if (!g_profiling) return;
+    if (!s.prof) return;
     cudaEventRecord(s.pev[2 * s.pcount + 1], s.stream);
     s.pcount++;
 }
@@ -776,6 +790,15 @@ static int enqueue_group(vsc_ctx* ctx, Slot* fr, int n, int dtype, const vsc_geo
     return VSC_OK;
 }
 
+static void CUDART_CB on_submission_done(void* p) {       // runs on a driver thread once the stream reaches it; no CUDA calls here
+    Slot* lead = static_cast<Slot*>(p);
+    {
+        std::lock_guard<std::mutex> lk(lead->owner->mu);
+        lead->done = true;
+    }
+    lead->owner->cv.notify_all();
+}
+
 static int submit_group_impl(vsc_ctx* ctx, int slot, int n, const uint8_t* const* rgb, const void* const* depth, int dtype,
                              int H, int W, const vsc_params* p, uint8_t* const* out, bool device_io) {
     if (!ctx) return fail(VSC_E_INVALID, "null context");
@@ -808,6 +831,11 @@ static int submit_group_impl(vsc_ctx* ctx, int slot, int n, const uint8_t* const
     if (rc) { cudaStreamSynchronize(lead.stream); return rc; }
     for (int i = 0; i < n; i++)
         if (fr[i].l_host_out) CU(cudaMemcpyAsync(fr[i].l_host_out, fr[i].l_out, nout, cudaMemcpyDeviceToHost, lead.stream));
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        lead.done = false;
+    }
+    CU(cudaLaunchHostFunc(lead.stream, on_submission_done, &lead));
     lead.busy = true;
     lead.nfr = n;
     lead.l_dtype = dtype; lead.l_H = H; lead.l_W = W; lead.l_p = *p;
@@ -877,6 +905,24 @@ extern "C" int vsc_query(vsc_ctx* ctx, int slot) {
     if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) return 0;
     return fail(VSC_E_CUDA, "stream query failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int vsc_wait_any(vsc_ctx* ctx, const int* slots, int n, int timeout_ms, int* which) {
+    if (!ctx || !slots || !which || n < 1) return fail(VSC_E_INVALID, "bad argument");
+    *which = -1;
+    for (int i = 0; i < n; i++) {
+        Slot* fr = group_lead(ctx, slots[i]);
+        if (!fr) return fail(VSC_E_INVALID, "slot %d out of range", slots[i]);
+        if (!fr->busy) return fail(VSC_E_STATE, "slot %d has no frame in flight", slots[i]);
+    }
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    while (true) {
+        for (int i = 0; i < n; i++)
+            if (group_lead(ctx, slots[i])->done) { *which = slots[i]; return VSC_OK; }
+        if (timeout_ms < 0) ctx->cv.wait(lk);
+        else if (ctx->cv.wait_until(lk, deadline) == std::cv_status::timeout) return VSC_OK;      // *which stays -1
+    }
 }
 
 extern "C" int vsc_sync(vsc_ctx* ctx) {
@@ -1196,7 +1242,7 @@ extern "C" int vsc_debug_fetch(vsc_ctx* ctx, int which, void* dst, size_t bytes)
 extern "C" int vsc_set_profiling(vsc_ctx* ctx, int on) {
     if (!ctx) return fail(VSC_E_INVALID, "null context");
     ctx->profiling = on != 0;
-    g_profiling = ctx->profiling;
+    for (auto& s : ctx->slots) s.prof = ctx->profiling;
     return VSC_OK;
 }
 // per-kernel device times of the last completed frame on `slot` (needs vsc_set_profiling(ctx,1) before submit)

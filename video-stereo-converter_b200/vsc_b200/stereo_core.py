@@ -214,6 +214,35 @@ class StereoGenerator:
             _lib.depth_code(pins[0][2].array.dtype), h, w, C.byref(_lib.make_params(p)), vp(*[x[3].array.ctypes.data for x in pins])))
         self._pending[slot] = n
 
+    def submit_host(self, slot: int, frames, params: StereoParams | None = None) -> None:
+        """Enqueue H2D + kernels + D2H for up to `group_size` caller-owned (rgb, depth) arrays WITHOUT staging copies:
+        the arrays are read by the copy engine directly (page-locked memory, e.g. _lib.PinnedBuffer, makes that copy
+        asynchronous) and must stay untouched until the slot is collected.  Results land in the slot's pinned outputs."""
+        p = params or self._DEFAULT_PARAMS
+        frames = list(frames)
+        n = len(frames)
+        if not 1 <= n <= self.group_size:
+            raise ValueError(f'a slot takes 1..{self.group_size} frames per submission')
+        if self._pending[slot] is not None:
+            raise RuntimeError(f'slot {slot} has an uncollected frame')
+        h, w = frames[0][0].shape[:2]
+        dt = frames[0][1].dtype
+        for rgb, depth in frames:
+            if (rgb.dtype != np.uint8 or rgb.shape != (h, w, 3) or depth.shape != (h, w) or depth.dtype != dt
+                    or not rgb.flags.c_contiguous or not depth.flags.c_contiguous):
+                raise ValueError('submit_host needs C-contiguous uint8 [H,W,3] frames and [H,W] depth maps of one size and dtype')
+        outs = []
+        for i in range(n):
+            self.pinned_inputs(slot, h, w, dt, i)
+            outs.append(self._pinned[slot][i][3].array.ctypes.data)
+        vp = C.c_void_p * n
+        _lib.check(self._lib.vsc_submit_group(
+            self._ctx.handle, slot, n, vp(*[f[0].ctypes.data for f in frames]), vp(*[f[1].ctypes.data for f in frames]),
+            _lib.depth_code(dt), h, w, C.byref(_lib.make_params(p)), vp(*outs)))
+        self._pending[slot] = n
+        self._held = getattr(self, '_held', {})
+        self._held[slot] = frames            # keep the arrays alive until collect()
+
     def submit(self, slot: int, rgb: np.ndarray, depth: np.ndarray, params: StereoParams | None = None) -> None:
         """Copy one frame into the slot's pinned staging buffers and enqueue H2D + kernels + D2H."""
         self.submit_frames(slot, [(rgb, depth)], params)
@@ -244,6 +273,7 @@ class StereoGenerator:
             _lib.check(self._lib.vsc_wait(self._ctx.handle, slot))
         finally:
             self._pending[slot] = None
+            getattr(self, '_held', {}).pop(slot, None)
         outs = [self._pinned[slot][i][3].array for i in range(n)]
         if copy:
             outs = [o.copy() for o in outs]
@@ -278,17 +308,14 @@ class StereoGenerator:
         return r == 1
 
     def wait_any(self, slots) -> int:
-        """Block until one of the given in-flight slots has finished; returns that slot (not yet collected)."""
-        import time
+        """Sleep until one of the given in-flight slots has finished; returns that slot (not yet collected).
+        The wait happens inside the library on a condition variable (no polling, the GIL is released)."""
         slots = list(slots)
-        spins = 0
-        while True:
-            for s in slots:
-                if self.ready(s):
-                    return s
-            spins += 1
-            if spins > 50:
-                time.sleep(0.0002)
+        arr = (C.c_int * len(slots))(*slots)
+        which = C.c_int(-1)
+        while which.value < 0:
+            _lib.check(self._lib.vsc_wait_any(self._ctx.handle, arr, len(slots), 2000, C.byref(which)))
+        return int(which.value)
 
     # -- measurement -------------------------------------------------------------------------------
     def timer_begin(self) -> None:
