@@ -21,6 +21,7 @@ slot pipeline the way consecutive seconds of a video do, and the timed region is
                 duration with the pipeline full
   workloads     the same measurements for BASELINE.json configs[2] / [3]: the 4K (3840x2160, 16-bit depth) clip,
                 frame-sharded over the N GPUs like the headline
+  driver        frames/s of the drop-in frame loop on a synthetic workflow directory of real PNG files (rank 0, N = 1)
   cpu_baseline  the reference's CPU path timed on this box's host cores, bounded sample (rank 0, N = 1 only)
 --impl reference times the reference's own CPU implementation alone: the UNMODIFIED helper/stereo_core.py staged
 under oracle/_ref by oracle/make_ref.py (cpu_baseline.kind "reference"; every timed step one full 1080p frame), or,
@@ -323,12 +324,82 @@ def run_ours(args, rank, world, local_rank):
         out.update({k: v for k, v in head.items() if k not in ('metric', 'value', 'unit', 'ms_per_step', 'whole_path')})
         if extra is not None:
             out['workloads'] = {'4k': extra}
+        if world == 1 and not args.no_driver:
+            try:
+                out['driver'] = driver_fps()
+            except Exception as e:       # the kernels' numbers must not depend on the file-I/O demonstration
+                out['driver'] = {'error': f'{type(e).__name__}: {e}'}
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(sample_frames=args.cpu_frames)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def driver_fps(n_frames=192, n_png=48):
+    """The drop-in frame loop (video-stereo-converter_b200/sbs_generator.py: process_shard) on a synthetic workflow
+    directory of real files, rank 0 / N = 1 only: PNG decode of frames and depth maps by the loader pool, grouped
+    pinned submissions, and either the raw rgb24 hand-off to an encoder (--raw-sink) or sbs_*.png files.  Wall clock
+    around process_shard with a generator that has already seen the clip's first 24 frames (steady state of a long clip)."""
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    from pathlib import Path
+    import cv2
+    sys.path.insert(0, os.path.join(ROOT, 'video-stereo-converter_b200'))
+    import sbs_generator
+    from vsc_b200 import StereoParams
+    from vsc_b200.sharder import InOrderPublisher, RawFrameSink
+    wl = WORKLOADS['1080p']
+    H, W = wl['h'], wl['w']
+    base = '/dev/shm' if os.path.isdir('/dev/shm') and shutil.disk_usage('/dev/shm').free > (6 << 30) else None
+    wf = Path(tempfile.mkdtemp(prefix='vsc_bench_wf_', dir=base))
+    try:
+        for d in ('frames', 'depth_maps', 'sbs'):
+            (wf / d).mkdir()
+        distinct = make_frames(16, H, W, wl['dtype'], seed0=500)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+
+        def write(i):
+            rgb, depth = distinct[i % len(distinct)]
+            cv2.imwrite(str(wf / 'frames' / f'frame_{i:06d}.png'), cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR), [cv2.IMWRITE_PNG_COMPRESSION, 1])
+            cv2.imwrite(str(wf / 'depth_maps' / f'depth_frame_{i:06d}.png'), depth, [cv2.IMWRITE_PNG_COMPRESSION, 1])
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(write, range(n_frames)))
+        pairs = [(wf / 'frames' / f'frame_{i:06d}.png', wf / 'depth_maps' / f'depth_frame_{i:06d}.png', f'{i:06d}') for i in range(n_frames)]
+        io_threads = max(2, cores - 2)
+        out = {'workload': f'{n_frames} files {W}x{H} PNG + 8-bit PNG depth (16 distinct synthetic frames), default params',
+               'io_threads': io_threads, 'slots': 6, 'frames_per_slot': 4}
+        from vsc_b200 import StereoGenerator
+        gen = StereoGenerator('cuda:0', n_slots=6, group_size=4)      # one generator for the whole clip, as in the CLI
+        try:
+            warm = pairs[:24]          # first frames of a clip: context, buffers and page-locked staging come into being
+            ws = RawFrameSink(str(wf / 'warm.rgb'), len(warm), H, 2 * W)
+            sbs_generator.process_shard(warm, wf / 'sbs', StereoParams(), 0, 6, io_threads, 'none', True, None, ws,
+                                        {p[2]: i for i, p in enumerate(warm)}, 4, gen)
+            ws.close()
+            os.remove(wf / 'warm.rgb')
+            sink = RawFrameSink(str(wf / 'sbs.rgb'), n_frames, H, 2 * W)
+            t0 = time.perf_counter()
+            n = sbs_generator.process_shard(pairs, wf / 'sbs', StereoParams(), 0, 6, io_threads, 'none', True, None, sink,
+                                            {p[2]: i for i, p in enumerate(pairs)}, 4, gen)
+            complete = sink.close()
+            dt = time.perf_counter() - t0
+            out['raw_sink'] = {'value': n / dt, 'unit': 'frames/s', 'frames': n, 'complete': bool(complete), 'seconds': dt}
+            os.remove(wf / 'sbs.rgb')
+            sub = pairs[:n_png]
+            pub = InOrderPublisher([str(wf / 'sbs' / f'sbs_{p[2]}.png') for p in sub])
+            t0 = time.perf_counter()
+            n = sbs_generator.process_shard(sub, wf / 'sbs', StereoParams(), 0, 6, io_threads, 'none', True, gen=gen)
+            ok = pub.run(timeout_s=30)
+            dt = time.perf_counter() - t0
+            out['png_files'] = {'value': n / dt, 'unit': 'frames/s', 'frames': n, 'complete': bool(ok), 'seconds': dt}
+        finally:
+            gen.close()
+        return out
+    finally:
+        shutil.rmtree(wf, ignore_errors=True)
 
 
 def _use_all_host_threads():
@@ -448,6 +519,7 @@ def main():
     ap.add_argument('--no-4k', action='store_true', help='skip the 4K workload')
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-driver', action='store_true', help='skip the file-based frame-loop measurement (driver)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

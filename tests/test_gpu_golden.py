@@ -102,3 +102,61 @@ def test_sbs_generator_cli_end_to_end(tmp_path):
     # second run: nothing left
     r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive'], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'All frames already processed.' in r.stdout
+
+
+def test_sbs_generator_survives_an_unreadable_frame(tmp_path):
+    """One corrupt frame: it is reported and skipped, every other frame is written and visible, the run ends with exit
+    code 0 and a second run has nothing but that frame left (reference: sbs_generator.py:229-230)."""
+    n = 10
+    wf, frames = _make_workflow(tmp_path, n)
+    (wf / 'frames' / 'frame_000004.png').write_bytes(b'not a png')
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive', '--gpus', '1', '--slots', '2'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'Error loading 000004' in r.stdout and 'Skipped 1 frame' in r.stdout
+    assert sorted(p.name for p in (wf / 'sbs').iterdir()) == [f'sbs_{i:06d}.png' for i in range(n) if i != 4]
+
+
+def test_sbs_generator_raw_sink_and_free_space(tmp_path):
+    """--raw-sink: the frames arrive as raw rgb24 in clip order and equal the oracle's; free_space deletes inputs only
+    in PNG mode after publication (checked in a second run with free_space = all)."""
+    import cv2
+    n = 6
+    wf, frames = _make_workflow(tmp_path, n, h=64, w=96)
+    sink = tmp_path / 'out.rgb'
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive', '--gpus', '1', '--raw-sink', str(sink)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    raw = np.fromfile(sink, np.uint8).reshape(n, 64, 192, 3)
+    for i, (rgb, depth) in enumerate(frames):
+        assert np.array_equal(raw[i], O.process_frame(rgb, depth, O.Params())), i
+    cfg = json.loads((wf / 'config.json').read_text())
+    cfg['free_space']['sbs_generator'] = 'all'
+    (wf / 'config.json').write_text(json.dumps(cfg))
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_generator.py'), str(wf), '--no-interactive', '--gpus', '1'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert len(list((wf / 'sbs').glob('sbs_*.png'))) == n
+    assert not list((wf / 'frames').iterdir()) and not list((wf / 'depth_maps').iterdir())
+    got = cv2.cvtColor(cv2.imread(str(wf / 'sbs' / 'sbs_000002.png'), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    assert np.array_equal(got, raw[2])
+
+
+def test_sbs_sweep_cli(tmp_path):
+    """sbs_sweep.py end to end: a 2 x 2 grid plus an invalid corner, images equal the oracle's, refusal recorded."""
+    import cv2
+    wf, frames = _make_workflow(tmp_path, 2, h=64, w=96)
+    out = tmp_path / 'sweep'
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'sbs_sweep.py'), str(wf), '--frame', '0', '--out', str(out),
+                        '--param', 'max_disparity=5,40', '--param', 'convergence=-50,0'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads((out / 'sweep.json').read_text())['results']
+    assert len(res) == 4
+    for e in res:
+        p = O.Params(**e['params'])
+        if e['params']['max_disparity'] == 5.0 and e['params']['convergence'] == -50.0:
+            assert e['refused'] and not (out / f"sweep_{e['index']:04d}.png").exists()     # crop window left of the view
+            continue
+        assert e['refused'] is None and e['ms'] > 0
+        img = cv2.cvtColor(cv2.imread(str(out / f"sweep_{e['index']:04d}.png"), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        assert np.array_equal(img, O.process_frame(frames[0][0], frames[0][1], p))

@@ -60,6 +60,44 @@ def test_in_order_publisher(tmp_path):
     assert not list(tmp_path.glob('*.ready')) and not list(tmp_path.glob('.*.part'))
 
 
+def test_in_order_publisher_steps_over_skipped_frames_and_reports_publication(tmp_path):
+    """A frame that cannot be produced is reported with mark_skipped: the frames after it still become visible (the
+    reference logs an unreadable frame and carries on, sbs_generator.py:229-230), and on_published fires only after
+    the final rename (inputs may be deleted then, not before)."""
+    finals = [str(tmp_path / f'sbs_{i:06d}.png') for i in range(5)]
+    seen = []
+    pub = sharder.InOrderPublisher(finals, on_published=lambda i: seen.append((i, os.path.exists(finals[i]))))
+
+    def write(i):
+        with open(pub.staged_path(finals[i]), 'wb') as f:
+            f.write(b'x')
+        pub.mark_ready(finals[i])
+
+    write(0); write(2); write(3)
+    assert pub.publish_available() == 1                                # frame 1 unknown: 2 and 3 wait
+    pub.mark_skipped(finals[1])
+    assert pub.publish_available() == 3 and pub.skipped == [finals[1]]
+    pub.mark_skipped(finals[4])
+    assert pub.run(timeout_s=2) and pub.done()
+    assert sorted(p.name for p in tmp_path.glob('sbs_*.png')) == ['sbs_000000.png', 'sbs_000002.png', 'sbs_000003.png']
+    assert seen == [(0, True), (2, True), (3, True)]
+    assert not list(tmp_path.glob('.*.skip')) and not list(tmp_path.glob('*.ready'))
+    # two threads publishing the same list must neither skip nor crash
+    finals2 = [str(tmp_path / f'b_{i:06d}.png') for i in range(200)]
+    pub2 = sharder.InOrderPublisher(finals2)
+    import threading
+    ths = [threading.Thread(target=pub2.run, kwargs=dict(poll_s=0.001, timeout_s=10)) for _ in range(2)]
+    for t in ths:
+        t.start()
+    for f in finals2:
+        with open(pub2.staged_path(f), 'wb') as fh:
+            fh.write(b'y')
+        pub2.mark_ready(f)
+    for t in ths:
+        t.join()
+    assert pub2.done() and len(list(tmp_path.glob('b_*.png'))) == 200
+
+
 def test_sweep_parameter_grid():
     """sbs_sweep.py: slider names / ranges of sbs_tester.py:356-362, cartesian product."""
     sys.path.insert(0, PKG)

@@ -54,15 +54,22 @@ class InOrderPublisher:
     """Renames finished outputs into place strictly in the order of `final_paths`.
 
     Workers (any rank / process) call `staged_path(final)` to know where to write and
-    `mark_ready(final)` when the file is complete (an atomic rename to `<final>.ready`); one publisher
-    (rank 0) runs `publish_available()` / `run()` which moves `.ready` files to their final names in
-    order and stops at the first one that is not ready yet.
+    `mark_ready(final)` when the file is complete (an atomic rename to `<final>.ready`); a frame that cannot
+    be produced (unreadable input, failed save) is reported with `mark_skipped(final)` so that the frames
+    after it are not held back (the reference logs such a frame and carries on, sbs_generator.py:229-230).
+    One publisher (rank 0) runs `publish_available()` / `run()`, which moves `.ready` files to their final
+    names in order, steps over skipped ones and stops at the first frame that is neither.
+    `on_published(index)` runs after the final rename of a frame (the place to delete its inputs: not before
+    the output exists under its real name).  Safe to call from several threads.
     """
 
-    def __init__(self, final_paths: Sequence[str]):
+    def __init__(self, final_paths: Sequence[str], on_published: Optional[Callable[[int], None]] = None):
         self.final_paths = [str(p) for p in final_paths]
         self._next = 0
         self._stop = threading.Event()
+        self._lock = threading.Lock()
+        self._on_published = on_published
+        self.skipped: List[str] = []
 
     @staticmethod
     def staged_path(final: str) -> str:
@@ -73,21 +80,45 @@ class InOrderPublisher:
     def ready_path(final: str) -> str:
         return str(final) + '.ready'
 
+    @staticmethod
+    def skip_path(final: str) -> str:
+        d, b = os.path.split(str(final))
+        return os.path.join(d, '.' + b + '.skip')
+
     @classmethod
     def mark_ready(cls, final: str) -> None:
         os.replace(cls.staged_path(final), cls.ready_path(final))
 
+    @classmethod
+    def mark_skipped(cls, final: str) -> None:
+        with open(cls.skip_path(final), 'w'):
+            pass
+
     def publish_available(self) -> int:
         n = 0
-        while self._next < len(self.final_paths):
-            final = self.final_paths[self._next]
-            ready = self.ready_path(final)
-            if os.path.exists(ready):
-                os.replace(ready, final)
-            elif not os.path.exists(final):
-                break
-            self._next += 1
-            n += 1
+        with self._lock:
+            while self._next < len(self.final_paths):
+                final = self.final_paths[self._next]
+                ready, skip = self.ready_path(final), self.skip_path(final)
+                published = False
+                if os.path.exists(ready):
+                    try:
+                        os.replace(ready, final)
+                        published = True
+                    except FileNotFoundError:      # another publisher (process) was faster
+                        pass
+                elif os.path.exists(skip):
+                    try:
+                        os.remove(skip)
+                    except FileNotFoundError:
+                        pass
+                    self.skipped.append(final)
+                elif not os.path.exists(final):
+                    break
+                if published and self._on_published is not None:
+                    self._on_published(self._next)
+                self._next += 1
+                n += 1
         return n
 
     @property
@@ -97,9 +128,12 @@ class InOrderPublisher:
     def done(self) -> bool:
         return self._next >= len(self.final_paths)
 
-    def run(self, poll_s: float = 0.05, on_progress: Optional[Callable[[int], None]] = None, timeout_s: Optional[float] = None) -> bool:
+    def run(self, poll_s: float = 0.05, on_progress: Optional[Callable[[int], None]] = None, timeout_s: Optional[float] = None,
+            final: bool = False) -> bool:
+        """Publish until everything is visible, stop() is called (ignored when `final`: the last drain after the
+        workers have finished) or the timeout passes.  True if every frame is published or skipped."""
         t0 = time.time()
-        while not self.done() and not self._stop.is_set():
+        while not self.done() and (final or not self._stop.is_set()):
             if self.publish_available() and on_progress:
                 on_progress(self._next)
             if self.done():
