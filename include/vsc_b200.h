@@ -152,6 +152,14 @@ int vsc_stage_backend(vsc_ctx *ctx, const uint8_t *left, const uint8_t *right, i
                       int left_crop, int right_crop, int crop_w, int height, int width, double sharpen,
                       uint8_t *out_sbs);
 
+/* Depth-map post-processing of the producer stage (/root/reference/depth_map_generator.py:217-236):
+ * cv2.resize(depth f32 [h,w] -> [H,W], INTER_LINEAR), min/max normalise, x255 (bits 8) or x65535 (bits 16), round half to
+ * even.  vsc_stage_depth_post: host buffers, synchronous; *ok = 0 when the resized map is flat (the reference then writes
+ * no depth map at all).  vsc_depth_post_device: device buffers, enqueued on `slot`'s stream, so that a following
+ * vsc_submit_device on the same slot can read d_out as its depth input without the map ever leaving the GPU. */
+int vsc_stage_depth_post(vsc_ctx *ctx, const float *depth, int h, int w, int H, int W, int bits, void *out, int *ok);
+int vsc_depth_post_device(vsc_ctx *ctx, int slot, const float *d_depth, int h, int w, int H, int W, int bits, void *d_out);
+
 /* -------- the module-level helpers that stereo_core.__all__ exports (stereo_core.py:22-29) ---- */
 /* normalize_depth (stereo_core.py:71-88) on n floats */
 int vsc_stage_normalize_f32(vsc_ctx *ctx, const float *in, size_t n, float *out);

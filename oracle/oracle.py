@@ -243,6 +243,24 @@ def telea_two_pass(img: np.ndarray, mask: np.ndarray, radius: int = 3, return_or
     return (img, order[1:-1, 1:-1]) if return_order else img
 
 
+def resize_linear_f32(src: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.float32)
+    out = np.empty((out_h, out_w), np.float32)
+    lib().orc_resize_linear_f32(_p(src), src.shape[0], src.shape[1], out_h, out_w, _p(out))
+    return out
+
+
+def depth_post(depth: np.ndarray, size, bits: int = 16):
+    """depth_map_generator.py:217-236: bilinear resize to size = (width, height), min/max normalise, quantise.
+    Returns the u8 / u16 map, or None when the resized map is flat (the reference writes no file then)."""
+    depth = np.ascontiguousarray(depth, np.float32)
+    w, h = int(size[0]), int(size[1])
+    out = np.empty((h, w), np.uint16 if bits == 16 else np.uint8)
+    lib().orc_depth_post.restype = C.c_int
+    ok = lib().orc_depth_post(_p(depth), depth.shape[0], depth.shape[1], h, w, int(bits), _p(out))
+    return out if ok else None
+
+
 MARCH_STATS = ('generations', 'tasks', 'largest_bucket', 'sweeps', 'max_sweeps', 'sorted_buckets', 'max_distinct_t',
                'evaluations')
 

@@ -17,6 +17,7 @@
  *   helper/stereo_core.py:414-434  _sharpen_image             -> orc_sharpen
  *   helper/stereo_core.py:298-299  F.interpolate(mode='area') -> orc_area_pool
  *   helper/stereo_core.py:253-254  cv2.resize(INTER_LANCZOS4) -> orc_lanczos4_h_*
+ *   depth_map_generator.py:217-236 depth post-processing      -> orc_depth_post
  *
  * Third-party arithmetic that is NOT under /root/reference is restated from the libraries'
  * published algorithms: OpenCV 4.13.0 (unpinned in requirements.txt:2)
@@ -929,4 +930,61 @@ ORC_API void orc_area_pool(const float *src, int C, int H, int W, int oH, int oW
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Depth-map post-processing on the producer side (/root/reference/depth_map_generator.py:217-236, SURVEY.md 8(f)
+ * rank 3): cv2.resize(depth f32, (W, H), INTER_LINEAR) -> min / max -> (d - min) / range -> * 255 | 65535 -> round
+ * half to even -> u8 | u16.  Returns 0 (nothing written) when the resized map is flat, like the reference.
+ * OpenCV imgproc/resize.cpp, 32F linear: scale = 1 / (dst / src) in double; fx = float((dx + 0.5) * scale - 0.5);
+ * sx = floor(fx), fx -= sx; sx < 0 -> (0, 0); sx >= src - 1 -> (src - 1, 0); taps (1 - fx, fx) in float;
+ * horizontal pass S[sx] * a0 + S[sx + 1] * a1, then vertical R0 * b0 + R1 * b1, every product and sum rounded to float
+ * (OpenCV's own code, cv2.ipp.setUseIPP(False): bit-exact except the first / last output rows when they clamp, where
+ * its single-row SIMD path fuses the multiply-add, <= 1 ulp; the IPP build that ships differs by up to 5e-6 relative).
+ * ---------------------------------------------------------------------------------------- */
+static void linear_axis(int ssize, int dsize, int *ofs, float *a0, float *a1) {
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    for (int d = 0; d < dsize; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(fx);
+        fx -= (float)s;
+        if (s < 0) { fx = 0.f; s = 0; }
+        if (s >= ssize - 1) { fx = 0.f; s = ssize - 1; }
+        ofs[d] = s; a0[d] = 1.f - fx; a1[d] = fx;
+    }
+}
+ORC_API void orc_resize_linear_f32(const float *src, int h, int w, int H, int W, float *dst) {
+    int *ox = malloc(sizeof(int) * W), *oy = malloc(sizeof(int) * H);
+    float *ax0 = malloc(sizeof(float) * W), *ax1 = malloc(sizeof(float) * W), *ay0 = malloc(sizeof(float) * H), *ay1 = malloc(sizeof(float) * H);
+    linear_axis(w, W, ox, ax0, ax1);
+    linear_axis(h, H, oy, ay0, ay1);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        const float *r0 = src + (size_t)oy[y] * w, *r1 = src + (size_t)(oy[y] + 1 < h ? oy[y] + 1 : h - 1) * w;
+        for (int x = 0; x < W; x++) {
+            const int x0 = ox[x], x1 = x0 + 1 < w ? x0 + 1 : w - 1;
+            const float t0 = r0[x0] * ax0[x], t1 = r0[x1] * ax1[x], top = t0 + t1;
+            const float u0 = r1[x0] * ax0[x], u1 = r1[x1] * ax1[x], bot = u0 + u1;
+            const float v0 = top * ay0[y], v1 = bot * ay1[y];
+            dst[(size_t)y * W + x] = v0 + v1;
+        }
+    }
+    free(ox); free(oy); free(ax0); free(ax1); free(ay0); free(ay1);
+}
+ORC_API int orc_depth_post(const float *src, int h, int w, int H, int W, int bits, void *dst) {
+    const size_t n = (size_t)H * W;
+    float *r = malloc(sizeof(float) * n);
+    orc_resize_linear_f32(src, h, w, H, W, r);
+    float mn = r[0], mx = r[0];
+    for (size_t i = 1; i < n; i++) { mn = r[i] < mn ? r[i] : mn; mx = r[i] > mx ? r[i] : mx; }
+    const float range = mx - mn;
+    if (!(range > 0.f)) { free(r); return 0; }
+    const float q = bits == 16 ? 65535.f : 255.f;
+    for (size_t i = 0; i < n; i++) {
+        const float nv = (r[i] - mn) / range;
+        const float v = rintf(nv * q);
+        if (bits == 16) ((uint16_t *)dst)[i] = (uint16_t)v; else ((uint8_t *)dst)[i] = (uint8_t)v;
+    }
+    free(r);
+    return 1;
 }

@@ -316,3 +316,45 @@ def test_backend_bit_exact(ctx, hs, ws, h, w, lc, rc, cw, sharp):
         halves.append(O.to_u8_trunc(v.transpose(1, 2, 0)))
     ref = np.hstack(halves)
     assert np.array_equal(out, ref), f'{(out != ref).sum()} values differ, max {np.abs(out.astype(int) - ref).max()}'
+
+
+@pytest.mark.parametrize('h,w,H,W,bits', [(153, 153, 108, 192, 16), (96, 128, 270, 480, 8), (384, 384, 1080, 1920, 16), (77, 131, 50, 60, 8)])
+def test_depth_post_bit_exact(ctx, h, w, H, W, bits):
+    """Producer-side depth post-processing through the C ABI: identical to the oracle."""
+    from vsc_b200 import StereoGenerator
+    rng = np.random.default_rng(h + bits)
+    import cv2
+    src = cv2.GaussianBlur(rng.random((h, w), dtype=np.float32) * 20 - 3, (0, 0), 3)
+    out = np.empty((H, W), np.uint16 if bits == 16 else np.uint8)
+    ok = C.c_int(0)
+    _lib.check(_lib.load().vsc_stage_depth_post(ctx.handle, _lib.ptr(src), h, w, H, W, bits, _lib.ptr(out), C.byref(ok)))
+    assert ok.value == 1 and np.array_equal(out, O.depth_post(src, (W, H), bits))
+    flat = np.full((h, w), 1.25, np.float32)
+    _lib.check(_lib.load().vsc_stage_depth_post(ctx.handle, _lib.ptr(flat), h, w, H, W, bits, _lib.ptr(out), C.byref(ok)))
+    ref = O.depth_post(flat, (W, H), bits)      # a flat input may come out of the float resize not quite flat: follow the oracle
+    assert bool(ok.value) == (ref is not None) and (ref is None or np.array_equal(out, ref))
+
+
+def test_depth_post_feeds_the_frame_on_the_device():
+    """Depth map post-processed on the slot's stream and consumed by vsc_submit_device without leaving the GPU: same
+    SBS frame as quantising on the host first."""
+    import torch
+    from vsc_b200 import StereoGenerator, StereoParams
+    rgb, _ = make_pair(108, 192, seed=4)
+    rng = np.random.default_rng(9)
+    import cv2
+    raw = cv2.GaussianBlur(rng.random((96, 96), dtype=np.float32) * 7, (0, 0), 5)
+    gen = StereoGenerator('cuda', n_slots=1)
+    try:
+        d_raw, d_rgb = torch.from_numpy(raw).cuda(), torch.from_numpy(rgb).cuda()
+        d_q = torch.empty((108, 192), dtype=torch.uint16, device='cuda')
+        d_out = torch.empty((108, 384, 3), dtype=torch.uint8, device='cuda')
+        torch.cuda.synchronize()
+        gen.depth_post_device(0, d_raw.data_ptr(), 96, 96, (192, 108), 16, d_q.data_ptr())
+        gen.submit_device(0, d_rgb.data_ptr(), d_q.data_ptr(), np.uint16, 108, 192, d_out.data_ptr(), StereoParams())
+        gen.wait(0)
+        q = O.depth_post(raw, (192, 108), 16)
+        assert np.array_equal(d_q.cpu().numpy().view(np.uint16), q)
+        assert np.array_equal(d_out.cpu().numpy(), O.process_frame(rgb, q, O.Params()))
+    finally:
+        gen.close()

@@ -249,6 +249,7 @@ struct Slot {
     DevBuf tabs;        // lanczos + axis tables
     DevBuf scalars;     // FrameScalars
     DevBuf tstats;      // Telea phase counters (VSC_TELEA_STATS builds)
+    DevBuf dp_scalars;  // min / max of the depth post-processing stage
     FrameScalars* h_scalars = nullptr;   // pinned mirror
     // table cache key
     int kH = 0, kW = 0, kSW = 0, kHs = 0, kWs = 0;
@@ -418,6 +419,7 @@ extern "C" void vsc_destroy(vsc_ctx* ctx) {
                           &s.qidx[0], &s.qidx[1], &s.tabs, &s.scalars};
         for (DevBuf* b : bufs) b->release();
         s.tstats.release();
+        s.dp_scalars.release();
         for (cudaEvent_t e : s.pev) cudaEventDestroy(e);
         if (s.h_scalars) cudaFreeHost(s.h_scalars);
         if (s.ev0) cudaEventDestroy(s.ev0);
@@ -1208,6 +1210,56 @@ extern "C" int vsc_stage_warp_f32(vsc_ctx* ctx, const float* image, const float*
     CU(cudaMemcpyAsync(left_mask, m0.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(right_mask, m1.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
+    return VSC_OK;
+}
+
+// ---- depth-map post-processing (depth_map_generator.py:217-236): resize + normalise + quantise ---------------------
+static int enqueue_depth_post(vsc_ctx* ctx, Slot& s, cudaStream_t stream, const float* d_src, int h, int w, int H, int W, int bits, void* d_dst) {
+    if (s.dp_scalars.ensure(sizeof(DepthPostScalars))) return VSC_E_NOMEM;
+    DepthPostScalars* sc = s.dp_scalars.as<DepthPostScalars>();
+    const double sx = 1.0 / ((double)W / (double)w), sy = 1.0 / ((double)H / (double)h);
+    dim3 grid((W + kThreads - 1) / kThreads, H);
+    depth_post_init_kernel<<<1, 1, 0, stream>>>(sc);
+    if (bits == 16) {
+        depth_post_kernel<0, uint16_t><<<grid, kThreads, 0, stream>>>(d_src, h, w, H, W, sx, sy, sc, (uint16_t*)d_dst, 65535.f);
+        depth_post_kernel<1, uint16_t><<<grid, kThreads, 0, stream>>>(d_src, h, w, H, W, sx, sy, sc, (uint16_t*)d_dst, 65535.f);
+    } else {
+        depth_post_kernel<0, uint8_t><<<grid, kThreads, 0, stream>>>(d_src, h, w, H, W, sx, sy, sc, (uint8_t*)d_dst, 255.f);
+        depth_post_kernel<1, uint8_t><<<grid, kThreads, 0, stream>>>(d_src, h, w, H, W, sx, sy, sc, (uint8_t*)d_dst, 255.f);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(VSC_E_CUDA, "depth post-processing launch failed: %s", cudaGetErrorString(e));
+    (void)ctx;
+    return VSC_OK;
+}
+static int depth_post_args_ok(const void* a, const void* b, int h, int w, int H, int W, int bits) {
+    if (!a || !b) return fail(VSC_E_INVALID, "null buffer");
+    if (h < 1 || w < 1 || H < 1 || W < 1 || (bits != 8 && bits != 16)) return fail(VSC_E_INVALID, "bad depth post-processing geometry / bit depth");
+    return VSC_OK;
+}
+extern "C" int vsc_depth_post_device(vsc_ctx* ctx, int slot, const float* d_depth, int h, int w, int H, int W, int bits, void* d_out) {
+    Slot* fr = group_lead(ctx, slot);
+    if (!fr) return fail(VSC_E_INVALID, "bad context or slot");
+    int rc = depth_post_args_ok(d_depth, d_out, h, w, H, W, bits);
+    if (rc) return rc;
+    if (fr->busy) return fail(VSC_E_STATE, "slot %d still has frames in flight; call vsc_wait first", slot);
+    CU(cudaSetDevice(ctx->device));
+    return enqueue_depth_post(ctx, *fr, fr->stream, d_depth, h, w, H, W, bits, d_out);
+}
+extern "C" int vsc_stage_depth_post(vsc_ctx* ctx, const float* depth, int h, int w, int H, int W, int bits, void* out, int* ok) {
+    STAGE_BEGIN();
+    int rc = depth_post_args_ok(depth, out, h, w, H, W, bits);
+    if (rc) return rc;
+    const size_t nin = (size_t)h * w * 4, nout = (size_t)H * W * (bits == 16 ? 2 : 1);
+    Tmp din, dout;
+    if (din.alloc(nin) || dout.alloc(nout)) return VSC_E_NOMEM;
+    CU(cudaMemcpyAsync(din.p, depth, nin, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = enqueue_depth_post(ctx, s, s.stream, (const float*)din.p, h, w, H, W, bits, dout.p))) return rc;
+    DepthPostScalars sc;
+    CU(cudaMemcpyAsync(out, dout.p, nout, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(&sc, s.dp_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    if (ok) *ok = ord2f(sc.max_ord) - ord2f(sc.min_ord) > 0.f;     // flat map: the reference writes no depth file
     return VSC_OK;
 }
 

@@ -23,7 +23,7 @@ EXPORTS = [
     'vsc_num_slots', 'vsc_geometry', 'vsc_process_frame', 'vsc_host_alloc', 'vsc_host_free', 'vsc_submit',
     'vsc_wait', 'vsc_query', 'vsc_wait_any', 'vsc_submit_device', 'vsc_sync', 'vsc_slot_stream', 'vsc_slot_elapsed_ms', 'vsc_slot_launches',
     'vsc_stage_lanczos', 'vsc_stage_depth', 'vsc_stage_warp', 'vsc_stage_bilateral', 'vsc_stage_inpaint',
-    'vsc_stage_backend', 'vsc_stage_warp_f32', 'vsc_stage_normalize_f32', 'vsc_stage_gamma_f32',
+    'vsc_stage_backend', 'vsc_stage_depth_post', 'vsc_depth_post_device', 'vsc_stage_warp_f32', 'vsc_stage_normalize_f32', 'vsc_stage_gamma_f32',
     'vsc_set_profiling', 'vsc_slot_kernel_times', 'vsc_timer_begin', 'vsc_timer_end', 'vsc_debug_fetch',
     'vsc_debug_telea_state', 'vsc_debug_telea_stats', 'vsc_debug_set_telea_capacity',
 ]
@@ -77,6 +77,8 @@ def load():
     lib.vsc_device.argtypes = [vp]
     lib.vsc_num_slots.argtypes = [vp]
     lib.vsc_geometry.argtypes = [i, i, C.POINTER(VscParams), C.POINTER(VscGeom)]
+    lib.vsc_stage_depth_post.argtypes = [vp, vp, i, i, i, i, i, vp, C.POINTER(C.c_int)]
+    lib.vsc_depth_post_device.argtypes = [vp, i, vp, i, i, i, i, i, vp]
     lib.vsc_wait_any.argtypes = [vp, C.POINTER(C.c_int), i, i, C.POINTER(C.c_int)]
     lib.vsc_process_frame.argtypes = [vp, vp, vp, i, i, i, C.POINTER(VscParams), vp]
     lib.vsc_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]

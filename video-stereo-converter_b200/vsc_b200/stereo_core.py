@@ -317,6 +317,23 @@ class StereoGenerator:
             _lib.check(self._lib.vsc_wait_any(self._ctx.handle, arr, len(slots), 2000, C.byref(which)))
         return int(which.value)
 
+    # -- producer-side depth post-processing (depth_map_generator.py:217-236) ------------------------
+    def depth_post(self, depth: np.ndarray, size, bits: int = 16) -> Optional[np.ndarray]:
+        """Bilinear resize of a float depth map to size = (width, height), min/max normalisation and quantisation to
+        uint8 / uint16, as the reference's depth stage does before writing the file.  None if the map is flat."""
+        d = np.ascontiguousarray(depth, np.float32)
+        w, h = int(size[0]), int(size[1])
+        out = np.empty((h, w), np.uint16 if bits == 16 else np.uint8)
+        ok = C.c_int(0)
+        _lib.check(self._lib.vsc_stage_depth_post(self._ctx.handle, _lib.ptr(d), d.shape[0], d.shape[1], h, w, int(bits), _lib.ptr(out), C.byref(ok)))
+        return out if ok.value else None
+
+    def depth_post_device(self, slot: int, d_depth: int, h: int, w: int, size, bits: int, d_out: int) -> None:
+        """Device-resident variant on `slot`'s stream (raw device pointers): follow it with submit_device on the same
+        slot and the quantised depth map never leaves the GPU."""
+        _lib.check(self._lib.vsc_depth_post_device(self._ctx.handle, slot, C.c_void_p(d_depth), h, w, int(size[1]), int(size[0]), int(bits),
+                                                   C.c_void_p(d_out)))
+
     # -- measurement -------------------------------------------------------------------------------
     def timer_begin(self) -> None:
         _lib.check(self._lib.vsc_timer_begin(self._ctx.handle))
