@@ -281,3 +281,12 @@ def test_8k_band_aggressive(gen):
     _compare_full(gen, 256, 7680, np.uint16, kw)
     kw['super_sampling'] = 2.0
     _compare_full(gen, 128, 7680, np.uint16, kw)
+
+
+def test_8k_full_frame_sweep_point(gen):
+    """One FULL 7680x3840 frame of BASELINE.json configs[4]: max disparity, convergence -50, aggressive hole filling
+    (no edge softening, smoothing 5), 16-bit depth, super_sampling 1 (the largest the CPU side can check: the
+    reference itself needs > 60 GB of host memory beyond SS 2).  Bit-exact against the oracle."""
+    kw = dict(max_disparity=100.0, convergence=-50.0, super_sampling=1.0, edge_softness=0.0, depth_gamma=1.0,
+              artifact_smoothing=5.0)
+    _compare_full(gen, 3840, 7680, np.uint16, kw)
