@@ -29,6 +29,10 @@ namespace vsc {
 
 constexpr float MARCH_BUCKET_INV = 1.4285714285714286f; // 1 / 0.7 (bucket width < 1/sqrt(2), see header)
 constexpr int MARCH_SMEM_COUNTERS = 32768;
+#ifndef VSC_MARCH_B_WARPS
+#define VSC_MARCH_B_WARPS 12
+#endif
+constexpr int MARCH_B_WARPS = VSC_MARCH_B_WARPS;      // warps of a CTA that work on the colour stage
 
 struct MarchWin {            // per-warp 9x9 window around the pixel being inpainted
     unsigned img[81];
@@ -406,7 +410,10 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const MarchScr
 #endif
     unsigned next = MARCH_NONE;               // task handed over by the one I just finished
     unsigned prevp = 0, prevc = 0;            // its pixel and colour (my own store may not have reached L2 yet)
-    while (true) {
+    // A cluster rarely offers more than a handful of independent chains at a time; warps beyond that would only poll
+    // the ready list (and take issue slots from the frames that share the GPU).  They wait at the final barrier.
+    const int workers = min(NW, max(2, min(MARCH_B_WARPS, ntask / 64)));
+    while (wid < workers) {
         unsigned i = next;
         if (i == MARCH_NONE) {
             if (lane == 0) {
