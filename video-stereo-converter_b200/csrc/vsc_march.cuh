@@ -183,7 +183,9 @@ __device__ __forceinline__ void march_eval_load(const TeleaView& V, MarchEval& e
         if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
             const size_t nb = (size_t)yy * Ws + xx;
             e.tn[q] = V.tt[nb];
-            if (march_dom(V.st[nb])) e.in_[q] = V.pstate[nb] >= J;
+            const unsigned char s = V.st[nb];
+            const unsigned o = V.pstate[nb];        // initialised wherever a neighbour of a domain pixel can lie
+            e.in_[q] = march_dom(s) && o >= J;
         }
     }
     e.own = V.tt[p];
@@ -228,18 +230,23 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
             if (radix_sort<NW>(sc.ka, cur, sc.kb, sc.sa, n, nbits, kmin, sh)) S = sc.sa;
         }
         MSTAT_T1(st_sort);
-        // claims: the first popped neighbour (lowest pop rank, then lowest q) computes a pixel
+        // claims: the first popped neighbour (lowest pop rank, then lowest q) computes a pixel.  All loads of an entry are
+        // issued before the first use (the order words are initialised wherever a neighbour of a queue entry can lie)
         for (int e = tid; e < n; e += nt) {
             const unsigned p = S[e];
             const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
+            size_t nbq[4]; bool ok[4]; unsigned char sq[4]; unsigned oq[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int yy = y + nb_dy(q), xx = x + nb_dx(q);
-                if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
-                const size_t nb = (size_t)yy * Ws + xx;
-                if (!march_dom(V.st[nb])) continue;
-                if (V.pstate[nb] >= 0x80000000u) atomicMin(&V.pstate[nb], 0x80000000u + (unsigned)(e * 4 + q));
+                ok[q] = yy >= 0 && yy < Hs && xx >= 0 && xx < Ws;
+                nbq[q] = ok[q] ? (size_t)yy * Ws + xx : (size_t)p;
             }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { sq[q] = V.st[nbq[q]]; oq[q] = V.pstate[nbq[q]]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ok[q] && march_dom(sq[q]) && oq[q] >= 0x80000000u) atomicMin(&V.pstate[nbq[q]], 0x80000000u + (unsigned)(e * 4 + q));
         }
         __syncthreads();
         // ownership (a thread takes a contiguous range of pops so that one prefix sum orders all tasks)
@@ -248,15 +255,19 @@ __device__ int march_order(const TeleaView& V, MarchSh<NW>& sh, const MarchScrat
         for (int e = e0; e < e1; e++) {
             const unsigned p = S[e];
             const int y = (int)(p / (unsigned)Ws), x = (int)(p - (unsigned)y * (unsigned)Ws);
-            unsigned own = 0;
+            size_t nbq[4]; bool ok[4]; unsigned char sq[4]; unsigned oq[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int yy = y + nb_dy(q), xx = x + nb_dx(q);
-                if (yy < 0 || yy >= Hs || xx < 0 || xx >= Ws) continue;
-                const size_t nb = (size_t)yy * Ws + xx;
-                if (!march_dom(V.st[nb])) continue;
-                if (__ldcg(&V.pstate[nb]) == 0x80000000u + (unsigned)(e * 4 + q)) own |= 1u << q;    // L2: sees the atomics
+                ok[q] = yy >= 0 && yy < Hs && xx >= 0 && xx < Ws;
+                nbq[q] = ok[q] ? (size_t)yy * Ws + xx : (size_t)p;
             }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { sq[q] = V.st[nbq[q]]; oq[q] = __ldcg(&V.pstate[nbq[q]]); }      // L2: sees the atomics
+            unsigned own = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ok[q] && march_dom(sq[q]) && oq[q] == 0x80000000u + (unsigned)(e * 4 + q)) own |= 1u << q;
             sc.ka[e] = own;
             c += __popc(own);
         }

@@ -315,6 +315,10 @@ class StereoGenerator:
         which = C.c_int(-1)
         while which.value < 0:
             _lib.check(self._lib.vsc_wait_any(self._ctx.handle, arr, len(slots), 2000, C.byref(which)))
+            if which.value < 0:          # timed out: a faulted stream never runs its completion callback - surface the error
+                for s in slots:
+                    if self.ready(s):
+                        return s
         return int(which.value)
 
     # -- producer-side depth post-processing (depth_map_generator.py:217-236) ------------------------
