@@ -20,7 +20,8 @@ slot pipeline the way consecutive seconds of a video do, and the timed region is
                 its stream), against MEASURED_PEAKS.json hbm_gbs; `in_load_ms_per_launch` is the same kernel's
                 duration with the pipeline full
   workloads     the same measurements for BASELINE.json configs[2] / [3]: the 4K (3840x2160, 16-bit depth) clip,
-                frame-sharded over the N GPUs like the headline
+                frame-sharded over the N GPUs like the headline; and for one corner of configs[4]: 8K VR frames with
+                maximum disparity and aggressive hole filling (3 steps of 16 frames at most)
   driver        frames/s of the drop-in frame loop on a synthetic workflow directory of real PNG files (rank 0, N = 1)
   cpu_baseline  the reference's CPU path timed on this box's host cores, bounded sample (rank 0, N = 1 only)
 --impl reference times the reference's own CPU implementation alone: the UNMODIFIED helper/stereo_core.py staged
@@ -51,6 +52,15 @@ WORKLOADS = {
     '4k': dict(h=2160, w=3840, dtype=np.uint16, distinct=16,
                metric='SBS frames/sec (4K, 16-bit depth, default stereo params)',
                name='4K (3840x2160) synthetic clip, uint16 depth, full-width SBS, default config.json stereo params'),
+    # BASELINE.json configs[4]: one corner of the sbs_tester sweep (sbs_tester.py:356-362) on 8K VR frames - maximum
+    # disparity, convergence at its limit, no edge softening (sharp depth edges: wide disocclusions) and the largest
+    # artifact smoothing (15x15 bilateral window); super_sampling 1, the setting the CPU side can still check
+    '8k': dict(h=3840, w=7680, dtype=np.uint16, distinct=6,
+               metric='SBS frames/sec (8K VR 7680x3840, max disparity, aggressive hole filling)',
+               name='8K VR (7680x3840) synthetic frames, uint16 depth, max_disparity=100 convergence=-50 super_sampling=1 '
+                    'edge_softness=0 artifact_smoothing=5 depth_gamma=1 sharpen=14 (sbs_tester sweep corner)',
+               params=dict(max_disparity=100.0, convergence=-50.0, super_sampling=1.0, edge_softness=0.0, artifact_smoothing=5.0,
+                           depth_gamma=1.0, sharpen=14.0)),
 }
 
 
@@ -118,7 +128,7 @@ def run_workload(key, batch, slots, group, steps, warmup, rank, world, local_ran
     from vsc_b200 import StereoGenerator, StereoParams, _lib
     wl = WORKLOADS[key]
     H, W, DT = wl['h'], wl['w'], wl['dtype']
-    params = StereoParams()
+    params = StereoParams(**wl.get('params', {}))
     gen = StereoGenerator(f'cuda:{local_rank}', n_slots=slots, group_size=group)
     n_distinct = min(wl['distinct'], max(batch, slots))
     frames = make_frames(n_distinct, H, W, DT, seed0=rank * 1000)          # this rank's frame range of the synthetic clip
@@ -316,6 +326,9 @@ def run_ours(args, rank, world, local_rank):
     extra = None
     if not args.no_4k:
         extra = run_workload('4k', args.batch_4k, args.slots_4k, args.group, args.steps, args.warmup, rank, world, local_rank, dist, True)
+    sweep = None
+    if not args.no_8k:
+        sweep = run_workload('8k', 16, 4, 2, max(1, min(args.steps, 3)), 1, rank, world, local_rank, dist, True)
     out = None
     if rank == 0:
         out = {'metric': head['metric'], 'value': head['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
@@ -324,6 +337,8 @@ def run_ours(args, rank, world, local_rank):
         out.update({k: v for k, v in head.items() if k not in ('metric', 'value', 'unit', 'ms_per_step', 'whole_path')})
         if extra is not None:
             out['workloads'] = {'4k': extra}
+        if sweep is not None:
+            out.setdefault('workloads', {})['8k'] = sweep
         if world == 1 and not args.no_driver:
             try:
                 out['driver'] = driver_fps()
@@ -517,6 +532,7 @@ def main():
     ap.add_argument('--batch-4k', type=int, default=64, help='4K frames per step per GPU')
     ap.add_argument('--slots-4k', type=int, default=10, help='slots per GPU at 4K (2.75 GB per frame in flight)')
     ap.add_argument('--no-4k', action='store_true', help='skip the 4K workload')
+    ap.add_argument('--no-8k', action='store_true', help='skip the 8K sweep-corner workload')
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-driver', action='store_true', help='skip the file-based frame-loop measurement (driver)')
