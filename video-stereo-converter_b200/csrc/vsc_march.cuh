@@ -423,7 +423,8 @@ __device__ void march_colour(const TeleaView& V, MarchSh<NW>& sh, const MarchScr
     unsigned prevp = 0, prevc = 0;            // its pixel and colour (my own store may not have reached L2 yet)
     // A cluster rarely offers more than a handful of independent chains at a time; warps beyond that would only poll
     // the ready list (and take issue slots from the frames that share the GPU).  They wait at the final barrier.
-    const int workers = min(NW, max(2, min(MARCH_B_WARPS, ntask / 64)));
+    // (wide disocclusions - clusters of tens of thousands of pixels - do offer more: every warp works on those)
+    const int workers = ntask > MARCH_SMEM_COUNTERS ? NW : min(NW, max(2, min(MARCH_B_WARPS, ntask / 64)));
     while (wid < workers) {
         unsigned i = next;
         if (i == MARCH_NONE) {
