@@ -2,6 +2,13 @@
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t_r02_final.log 2>&1; tail -2 gpurun_out/t_r02_final.log
 timeout 900 python bench.py > gpurun_out/bench_r02_n1.json 2> gpurun_out/bench_r02_n1.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_reference.json 2> gpurun_out/bench_r02_reference.err
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-driver --no-4k > gpurun_out/plain_launches.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02_1080p.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-driver --no-4k > gpurun_out/ncu_l2.log 2>&1
-for S in 12 14; do timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-driver --slots-4k $S > gpurun_out/bench_r02_4k_s$S.json 2> gpurun_out/bench_r02_4k_s$S.err; done
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-driver --no-4k --no-8k > gpurun_out/plain_launches.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02_1080p.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-driver --no-4k --no-8k > gpurun_out/ncu_l2.log 2>&1
+python tools/prof_one_frame.py 1080 1920 3 1 > gpurun_out/plain_r02w.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"depth_front|warp_kernel|bilateral|backend|telea_prepare|lanczos|normalize" -s 9 -c 9 -o gpurun_out/prof_r02_wide -f python tools/prof_one_frame.py 1080 1920 3 1 > gpurun_out/ncu_r02w.log 2>&1
+python tools/prof_one_frame.py 1080 1920 3 4 > gpurun_out/plain_r02m.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"telea_march_kernel" -s 2 -c 1 -o gpurun_out/prof_r02_march -f python tools/prof_one_frame.py 1080 1920 3 4 > gpurun_out/ncu_r02m.log 2>&1
+python tools/prof_one_frame.py 2160 3840 3 1 > gpurun_out/plain_r02k.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none -k regex:"depth_front|warp_kernel|bilateral|backend|telea_prepare|telea_march" -s 7 -c 7 -o gpurun_out/prof_r02_4k -f python tools/prof_one_frame.py 2160 3840 3 1 > gpurun_out/ncu_r02k.log 2>&1
+python tools/dbg_stats.py > gpurun_out/march_phases_r02_1080p.txt 2>&1
+python tools/soak_determinism.py 4 > gpurun_out/soak_r02.txt 2>&1; tail -1 gpurun_out/soak_r02.txt
