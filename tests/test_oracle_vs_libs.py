@@ -257,6 +257,32 @@ def test_depth_post_vs_cv2(h, w, H, W):
     assert O.depth_post(np.full((9, 9), 2.5, np.float32), (20, 12), 16) is None        # flat map: no depth file
 
 
+@pytest.mark.parametrize('seed', range(6))
+def test_march_model_random_masks(seed):
+    """Random mixtures of speckle, lines, blobs and border-touching bands: the generation schedule reproduces the
+    sequential march's arrival times and order on every one of them."""
+    rng = np.random.default_rng(100 + seed)
+    h, w = int(rng.integers(40, 110)), int(rng.integers(40, 140))
+    m = (rng.random((h, w)) < rng.choice([0.0, 0.01, 0.05])).astype(np.uint8) * 255
+    for _ in range(int(rng.integers(0, 6))):
+        p0 = (int(rng.integers(0, w)), int(rng.integers(0, h))); p1 = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+        cv2.line(m, p0, p1, 255, int(rng.integers(1, 6)))
+    for _ in range(int(rng.integers(0, 4))):
+        cv2.circle(m, (int(rng.integers(0, w)), int(rng.integers(0, h))), int(rng.integers(2, 18)), 255, -1)
+    if seed % 2:
+        m[:, :int(rng.integers(1, 30))] = 255
+    if seed % 3 == 0:
+        m[-int(rng.integers(1, 12)):, :] = 255
+    if not m.any():
+        m[h // 2, w // 2] = 255
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    _, t = O.telea(img, m, 3, return_t=True)
+    _, order = O.telea_two_pass(img, m, 3, return_order=True)
+    t2, order2, stats = O.march_model(m)
+    assert np.array_equal(t.view(np.uint32), t2.view(np.uint32)) and np.array_equal(order, order2)
+    assert stats['max_sweeps'] <= 10
+
+
 def test_telea_known_answers():
     """const-101 image with a 1-px hole inpaints to 102 (+0.5 and round both apply), const-100 to 100."""
     for val, want in ((101, 102), (100, 100)):

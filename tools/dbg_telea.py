@@ -7,7 +7,6 @@ import oracle as O
 from vsc_b200 import _lib
 from vsc_b200.synthetic import make_rgb
 lib = _lib.load()
-lib.vsc_debug_telea_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
 ctx = _lib.Context(0, 1)
 def run(img, hole, name):
     h, w = hole.shape
@@ -19,7 +18,7 @@ def run(img, hole, name):
         _lib.check(lib.vsc_stage_inpaint(ctx.handle, _lib.ptr(out), _lib.ptr(valid), h, w, 0, w))
         outs.append(out)
     tt = np.empty((h, w), np.float32); st = np.empty((h, w), np.uint8)
-    _lib.check(lib.vsc_debug_telea_state(ctx.handle, 0, _lib.ptr(tt), _lib.ptr(st), h * w))
+    _lib.check(lib.vsc_debug_telea_state(ctx.handle, 0, _lib.ptr(tt), _lib.ptr(st), None, h * w))
     mask = ((1 - valid.astype(np.float32)) * 255).astype(np.uint8)
     M = O.dilate3(mask)
     ref, t = O.telea(img, M, 3, return_t=True)
