@@ -879,6 +879,10 @@ extern "C" int vsc_wait(vsc_ctx* ctx, int slot) {
         if (e != cudaSuccess) { lead.busy = false; return fail(VSC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
         overflow = false;
         for (int i = 0; i < n; i++)
+            if (fr[i].h_scalars->overflow == 0x7fffffff) {      // raised by the march itself, never by a size
+                lead.busy = false;
+                return fail(VSC_E_STATE, "internal invariant of the hole-filling march violated (bucket range); please report the frame");
+            }
             if (fr[i].h_scalars->overflow) {
                 // Telea queue scratch was too small for this frame's holes: grow it and redo the submission
                 const size_t need = (size_t)fr[i].h_scalars->overflow;
@@ -1136,6 +1140,8 @@ extern "C" int vsc_stage_inpaint(vsc_ctx* ctx, uint8_t* img, const uint8_t* vali
         CU(cudaMemcpyAsync(s.h_scalars, s.scalars.p, sizeof(FrameScalars), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
         if (!s.h_scalars->overflow) break;
+        if (s.h_scalars->overflow == 0x7fffffff)
+            return fail(VSC_E_STATE, "internal invariant of the hole-filling march violated (bucket range); please report the frame");
         s.qcap = (size_t)s.h_scalars->overflow * 5 / 4 + 1024;
     }
     if (s.h_scalars->overflow) return fail(VSC_E_NOMEM, "hole-filling scratch overflow persisted");
