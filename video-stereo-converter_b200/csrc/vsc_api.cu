@@ -878,7 +878,7 @@ extern "C" int vsc_wait(vsc_ctx* ctx, int slot) {
         cudaError_t e = cudaStreamSynchronize(lead.stream);
         if (e != cudaSuccess) { lead.busy = false; return fail(VSC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
         overflow = false;
-        for (int i = 0; i < n; i++)
+        for (int i = 0; i < n; i++) {
             if (fr[i].h_scalars->overflow == 0x7fffffff) {      // raised by the march itself, never by a size
                 lead.busy = false;
                 return fail(VSC_E_STATE, "internal invariant of the hole-filling march violated (bucket range); please report the frame");
@@ -889,6 +889,7 @@ extern "C" int vsc_wait(vsc_ctx* ctx, int slot) {
                 fr[i].qcap = need + need / 4 + 1024;
                 overflow = true;
             }
+        }
         if (!overflow) break;
         vsc_geom g;
         int rc = vsc_geometry(lead.l_H, lead.l_W, &lead.l_p, &g);
