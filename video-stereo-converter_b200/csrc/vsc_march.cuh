@@ -3,8 +3,9 @@
 // (clusters: vsc_telea.cuh).  The reference pops a sorted list one pixel at a time and re-reads pixels it has just
 // written; here the same result is produced in two stages:
 //
-//   A. ORDER.  The arrival times T and the order in which hole pixels are computed depend on the mask alone.  Both
-//      fast-marching sweeps (outer distance ring, then the holes) run as bulk-synchronous GENERATIONS:
+//   A. ORDER.  The arrival times T and the order in which hole pixels are computed depend on the mask alone.  The two
+//      fast-marching sweeps of the reference (outer distance ring, then the holes) are independent - a ring pixel and a
+//      hole pixel are never 4-neighbours, the band separates them - and run as ONE march in bulk-synchronous GENERATIONS:
 //        bucket g   = queue entries with floor(T / 0.7) == g.  A pixel computed while bucket g is popped has
 //                     T in [popped T + 1/sqrt(2), popped T + 1], i.e. it belongs to bucket g+1 or g+2: three rotating
 //                     lists replace the sorted list and bucket g is complete before it is popped
@@ -16,12 +17,12 @@
 //                     thread re-evaluates its tasks until nothing changes - the fixed point is unique because the
 //                     dependencies follow J (measured: <= 7 sweeps; the test suite pins this schedule with a sequential CPU model)
 //      No queue, no per-pixel waiting: a generation is a handful of data-parallel phases.
-//   B. COLOURS.  The hole pixels are inpainted in the recorded order as ONE dataflow without generations or CTA
-//      barriers: "pixel q was known when pixel J was computed" is ord[q] < J.  A warp takes the next pixel, stages its
-//      9x9 window and computes the 28 weights BEFORE it waits (they do not depend on colours), then waits only for the
-//      earlier hole pixels inside the window that are still in flight.  Finished pixels publish (index, colour) as one
-//      64-bit word in a shared-memory ring, so the dependent chain of a crack runs through shared memory: poll,
-//      9 sums in the reference's raster order, division / square root, publish.
+//   B. COLOURS.  "Pixel q was known when pixel i was computed" is ord[q] < i, so the colours need no flags, no
+//      generations and no CTA barriers: they are a dataflow over the recorded order.  Every hole pixel counts the earlier
+//      hole pixels in its 9x9 window; pixels with count 0 are READY.  A warp only ever takes a ready pixel (window, 28
+//      weights with one tap per lane, 9 sums in the reference's raster order, division / square root) and then decrements
+//      the counters of the later hole pixels around it; the first one that reaches zero continues on the same warp - a
+//      crack is a chain, there is no hand-over - the others go to the ready list.  See march_colour.
 #pragma once
 #include "vsc_telea.cuh"
 
