@@ -160,3 +160,25 @@ def test_sbs_sweep_cli(tmp_path):
         assert e['refused'] is None and e['ms'] > 0
         img = cv2.cvtColor(cv2.imread(str(out / f"sweep_{e['index']:04d}.png"), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
         assert np.array_equal(img, O.process_frame(frames[0][0], frames[0][1], p))
+
+
+def test_bench_line_contract(tmp_path):
+    """bench.py on a small configuration: one JSON line with the contract's keys (value, e2e with copy bytes, roofline
+    with measured kernel time, workloads, cpu_baseline of the staged reference or the port), and the launch count."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '3', '--batch', '16', '--slots', '2',
+                        '--batch-4k', '4', '--slots-4k', '1', '--no-8k', '--no-driver', '--cpu-frames', '1'],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, VSC_BENCH_NO_CLOCKS='1'))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['unit'] == 'frames/s' and d['n_gpus'] == 1 and d['steps'] == 1 and d['higher_is_better'] is True and d['scaling'] == 'weak'
+    assert d['value'] > 0 and d['e2e']['value'] > 0 and d['vs_baseline'] is None
+    assert d['e2e']['h2d_bytes_per_step'] == 16 * (1080 * 1920 * 4) and d['e2e']['d2h_bytes_per_step'] == 16 * 1080 * 3840 * 3
+    rf = d['roofline']
+    assert rf['bound'] == 'hbm' and rf['kernel'].startswith('telea_') and 0 < rf['frac'] < 1 and rf['kernel_ms_per_launch'] > 0
+    assert rf['algorithmic_bytes_per_launch'] == 20736000 * rf['frames_per_launch']
+    assert d['gpu_launches'] > 0 and d['launches_per_frame'] < 16
+    w = d['workloads']['4k']
+    assert w['value'] > 0 and w['e2e']['value'] > 0 and w['roofline']['algorithmic_bytes_per_launch'] % 91238400 == 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['value'] > 0
