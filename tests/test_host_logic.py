@@ -265,3 +265,24 @@ def test_bench_reference_arm_prints_contract_line(force_port):
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert d['cpu_baseline']['kind'] in (('port',) if force_port else ('reference', 'port'))
     assert d['cpu_baseline']['cores'] >= 1 and d['value'] > 0
+
+
+def test_div3_identity(tmp_path):
+    """The back end divides the 3x3 pooling sums by 3 with a multiply and two FMAs (csrc/vsc_kernels.cuh div3_exact);
+    the identity is checked against the IEEE division for every float of the range on hosts with FMA hardware
+    (~20 s), on a 1/64 sample otherwise (software fmaf)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    here = os.path.dirname(os.path.abspath(__file__))
+    hw_fma = False
+    try:
+        hw_fma = ' fma ' in open('/proc/cpuinfo').read()
+    except OSError:
+        pass
+    exe = str(tmp_path / 'div3_check')
+    flags = ['-O2', '-ffp-contract=off'] + (['-mfma'] if hw_fma else [])
+    subprocess.run(['gcc'] + flags + ['-o', exe, os.path.join(here, 'div3_check.c'), '-lm'], check=True)
+    out = subprocess.run([exe, '1' if hw_fma else '64'], check=True, capture_output=True, text=True, timeout=600).stdout.split()
+    assert int(out[0]) == 0 and int(out[1]) > 1_000_000

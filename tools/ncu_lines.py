@@ -41,5 +41,6 @@ for (key, n) in per.most_common(top):
     if f not in src:
         p = os.path.join(srcdir, f)
         src[f] = open(p).read().splitlines() if os.path.exists(p) else []
-    text = src[f][ln - 1].strip() if ln - 1 < len(src[f]) else ''
+    ln2 = ln + int(os.environ.get('LINE_SHIFT', '0'))       # sources edited above since the build: shift the look-up
+    text = src[f][ln2 - 1].strip() if 0 <= ln2 - 1 < len(src[f]) else ''
     print(f'{n / 1e6:8.2f} M {100 * n / total:5.1f} %  {f}:{ln}  {text[:110]}')

@@ -529,7 +529,7 @@ static int run_depth_front(vsc_ctx* ctx, Slot& s, const vsc_geom& g, const vsc_p
         GaussTaps gt = gauss_taps(g.blur_k, p.edge_softness);
         const int r = g.blur_k / 2, AH = DF_T + 2 * r;
         // upsampled tile + horizontally blurred tile (also the staging area of the separable upsample) + row taps + pow tables
-        const size_t smem = ((size_t)AH * (AH + 1) + (size_t)AH * (DF_T + 1)) * 4 + (size_t)AH * sizeof(AxisTap) + kPowTabN * sizeof(double);
+        const size_t smem = ((size_t)AH * AH + (size_t)AH * DF_SB) * 4 + (size_t)AH * sizeof(AxisTap) + kPowTabN * sizeof(double);
         dim3 grid((g.ss_w + DF_T - 1) / DF_T, (g.ss_h + DF_T - 1) / DF_T);
         prof_begin(s, "depth_front_kernel");
         if (g.blur_k == 31)
@@ -565,7 +565,7 @@ static int run_warp(Slot& s, const vsc_geom& g, double max_disparity, const uint
     const int nsrc = a.TS + 2 * a.R + 8;
     const double ratio = a.upsample ? (double)g.stretched_w / (double)g.ss_w : 1.0;
     a.rgb_stage_bytes = (int)align_up((size_t)((int)(nsrc * ratio) + 8) * 3 + 32, 16);
-    const size_t smem = (size_t)4 * a.TS * 4 + 2 * ((size_t)a.TS * 4 + 16) + 2 * (size_t)a.rgb_stage_bytes;
+    const size_t smem = 2 * ((size_t)a.TS + 1) * 8 + 128 + 2 * ((size_t)a.TS * 4 + 16) + 2 * (size_t)a.rgb_stage_bytes;
     dim3 grid(nseg, g.ss_h);
     prof_begin(s, "warp_kernel");
     switch (mode) {
@@ -587,7 +587,7 @@ static int run_bilateral(vsc_ctx* ctx, Slot& s, int Hs, int Ws, double smoothing
     a.color_w = ctx->color_w.as<float>();
     a.Hs = Hs; a.Ws = Ws;
     const int TW = 32 + 2 * a.taps.radius;
-    const size_t smem = (768 + (size_t)TW * TW) * 4;
+    const size_t smem = ((a.taps.radius == 2 ? 3 * 768 : 768) + (size_t)TW * TW) * 4;
     dim3 grid((Ws + 31) / 32, (Hs + 31) / 32, nviews), block(32, 8);
     prof_begin(s, "bilateral_kernel");
     switch (a.taps.radius) {
