@@ -190,6 +190,10 @@ int vsc_debug_telea_state(vsc_ctx *ctx, int view, float *tt, uint8_t *st, uint32
 int vsc_debug_telea_stats(vsc_ctx *ctx, unsigned long long *out64);
 /* test hook: set the hole-filling queue capacity (entries per view) to exercise the overflow/re-run path */
 int vsc_debug_set_telea_capacity(vsc_ctx *ctx, size_t entries);
+/* device-side check of two arithmetic identities the kernels use instead of library calls, over every float of
+ * their range: which = 0 reciprocal (MUFU.RCP + one Newton step) against the correctly rounded 1/x on [1, 256);
+ * which = 1 x/3 by multiply + two FMAs against the IEEE quotient on [0, 2295].  *mismatches must come back 0. */
+int vsc_debug_selftest(vsc_ctx *ctx, int which, unsigned long long *mismatches);
 
 #ifdef __cplusplus
 }

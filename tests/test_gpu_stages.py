@@ -58,6 +58,8 @@ def _oracle_depth(depth_st, hs, ws, p):
     (70, 130, dict(super_sampling=1.0, edge_softness=7.5, depth_gamma=2.0)),
     (64, 150, dict(super_sampling=4.0, edge_softness=0.0, depth_gamma=0.1)),
     (200, 333, dict(super_sampling=1.7, edge_softness=30.0, depth_gamma=1.3)),
+    (81, 111, {}),                                                                   # odd super-sampled width (333): scalar stores, last column unpaired
+    (75, 131, dict(super_sampling=1.0, edge_softness=10.0, depth_gamma=0.7)),        # odd width, generic tap count
 ])
 def test_depth_front(ctx, h, sw, kw):
     p, cp = _params(**kw)
@@ -358,3 +360,13 @@ def test_depth_post_feeds_the_frame_on_the_device():
         assert np.array_equal(d_out.cpu().numpy(), O.process_frame(rgb, q, O.Params()))
     finally:
         gen.close()
+
+
+@pytest.mark.parametrize('which', [0, 1])
+def test_arithmetic_identities_on_the_device(ctx, which):
+    """The bilateral filter's reciprocal (MUFU.RCP + one Newton step, no range check) and the back end's division
+    by 3 (multiply + two FMAs, scalar and packed) replace correctly rounded library operations; the device compares
+    them with those operations for EVERY float of their range ([1, 256) and [0, 2295])."""
+    bad = C.c_ulonglong(123)
+    _lib.check(_lib.load().vsc_debug_selftest(ctx.handle, which, C.byref(bad)))
+    assert bad.value == 0

@@ -1295,6 +1295,28 @@ extern "C" int vsc_debug_fetch(vsc_ctx* ctx, int which, void* dst, size_t bytes)
     return VSC_OK;
 }
 
+// which = 0: rcp_rn_1_256 against __frcp_rn on [1, 256); which = 1: div3_exact / div3_exact2 against __fdiv_rn(x, 3)
+// on [0, 2295 + 16 ulp].  *mismatches = number of floats of the range where they differ (must be 0).
+extern "C" int vsc_debug_selftest(vsc_ctx* ctx, int which, unsigned long long* mismatches) {
+    if (!ctx || !mismatches || which < 0 || which > 1) return fail(VSC_E_INVALID, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, sizeof *d_bad));
+    cudaError_t e = cudaMemset(d_bad, 0, sizeof *d_bad);
+    if (e == cudaSuccess) {
+        const float top = 2295.0f;
+        unsigned tb;
+        memcpy(&tb, &top, 4);
+        const unsigned lo = which == 0 ? 0x3f800000u : 0u, hi = which == 0 ? 0x437fffffu : tb + 16u;
+        selftest_kernel<<<ctx->sm_count * 8, kThreads>>>(which, lo, hi, d_bad);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(mismatches, d_bad, sizeof *d_bad, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(VSC_E_CUDA, "selftest: %s", cudaGetErrorString(e));
+    return VSC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // measurement helpers
 // ------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ EXPORTS = [
     'vsc_stage_lanczos', 'vsc_stage_depth', 'vsc_stage_warp', 'vsc_stage_bilateral', 'vsc_stage_inpaint',
     'vsc_stage_backend', 'vsc_stage_depth_post', 'vsc_depth_post_device', 'vsc_stage_warp_f32', 'vsc_stage_normalize_f32', 'vsc_stage_gamma_f32',
     'vsc_set_profiling', 'vsc_slot_kernel_times', 'vsc_timer_begin', 'vsc_timer_end', 'vsc_debug_fetch',
-    'vsc_debug_telea_state', 'vsc_debug_telea_stats', 'vsc_debug_set_telea_capacity',
+    'vsc_debug_telea_state', 'vsc_debug_telea_stats', 'vsc_debug_set_telea_capacity', 'vsc_debug_selftest',
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.vsc_debug_telea_state.argtypes = [vp, i, vp, vp, vp, C.c_size_t]
     lib.vsc_debug_telea_stats.argtypes = [vp, vp]
     lib.vsc_debug_set_telea_capacity.argtypes = [vp, C.c_size_t]
+    lib.vsc_debug_selftest.argtypes = [vp, i, C.POINTER(C.c_ulonglong)]
     if lib.vsc_abi_version() != 1:
         raise ImportError('libvsc_b200.so ABI version mismatch')
     _lib = lib
